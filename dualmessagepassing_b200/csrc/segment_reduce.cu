@@ -1,0 +1,182 @@
+// segment_reduce.cu -- deterministic sorted-segment sum of edge rows (forward node aggregation and
+// the backward scatter of the endpoint gathers).  Replaces DGL's `fn.sum` gSpMM (dmpnn.py:92,163)
+// and autograd's atomic `index_add_`; see include/dmp_b200.h for the contract.
+//
+// Work decomposition: one group of G lanes per segment (G = 8/16/32 so that a 128-wide fp32 row is
+// exactly one float4 per lane of a full warp; narrower rows pack several segments per warp).  A lane
+// owns ITER column vectors and walks the segment's edge list in ascending position, keeping U rows
+// in flight (U independent 128-bit loads per lane) and adding them in order with __fadd_rn, so the
+// result equals a sequential CPU loop bit for bit.  The edge-id list is read with warp-broadcast
+// loads (one 32-bit word per group per edge); bit 31 of each entry is the reversed flag, so neither
+// the flag nor the sign needs a second gather.
+#include "common.cuh"
+
+namespace dmp {
+
+struct SegParams {
+  const int32_t* indptr;
+  const uint32_t* eid;
+  const float* w_perm;
+  const float* V;
+  int64_t ldV;
+  int64_t rev_off;
+  const float* base;
+  int64_t ld_base;
+  const float* bias;
+  float* out;
+  int64_t ld_out;
+  int64_t nseg;
+  int H;
+  int mode;
+};
+
+template <int VEC, int G, int ITER, int U>
+__global__ void __launch_bounds__(kThreads) segment_reduce_kernel(const SegParams p) {
+  constexpr int kGroups = kThreads / G;
+  const int lane = threadIdx.x % G;
+  const int64_t seg = (int64_t)blockIdx.x * kGroups + threadIdx.x / G;
+  if (seg >= p.nseg) return;
+
+  const int beg = __ldg(p.indptr + seg);
+  const int end = __ldg(p.indptr + seg + 1);
+  const bool sign_by_rev = (p.mode & DMP_SEG_SIGN_BY_REV) != 0;
+  const bool has_w = p.w_perm != nullptr;
+
+  int col[ITER];
+  bool ok[ITER];
+#pragma unroll
+  for (int it = 0; it < ITER; ++it) {
+    col[it] = (lane + it * G) * VEC;
+    ok[it] = col[it] < p.H;
+  }
+
+  float acc[ITER][VEC];
+#pragma unroll
+  for (int it = 0; it < ITER; ++it)
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) acc[it][k] = 0.0f;
+
+  for (int j = beg; j < end; j += U) {
+    uint32_t ef[U];
+    float w[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const bool valid = j + u < end;
+      ef[u] = valid ? __ldg(p.eid + j + u) : 0u;
+      w[u] = (valid && has_w) ? __ldg(p.w_perm + j + u) : 1.0f;
+    }
+    Row<VEC> v[U][ITER];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (j + u < end) {
+        const uint32_t r = ef[u] >> 31;
+        const float* row = p.V + (int64_t)(ef[u] & DMP_EID_MASK) * p.ldV + (r ? p.rev_off : 0);
+#pragma unroll
+        for (int it = 0; it < ITER; ++it)
+          if (ok[it]) v[u][it] = ld_stream<VEC>(row + col[it]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (j + u < end) {
+        const bool neg = sign_by_rev && (ef[u] >> 31) == 0;
+#pragma unroll
+        for (int it = 0; it < ITER; ++it) {
+          if (ok[it]) {
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+              float t = v[u][it].v[k];
+              if (neg) t = -t;
+              if (has_w) t = __fmul_rn(t, w[u]);
+              acc[it][k] = __fadd_rn(acc[it][k], t);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  const bool negate = (p.mode & DMP_SEG_NEGATE_OUT) != 0;
+#pragma unroll
+  for (int it = 0; it < ITER; ++it) {
+    if (!ok[it]) continue;
+    Row<VEC> r;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) r.v[k] = negate ? -acc[it][k] : acc[it][k];
+    if (p.base != nullptr) {
+      Row<VEC> b = ld_plain<VEC>(p.base + seg * p.ld_base + col[it]);  // base may alias out
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) r.v[k] = __fadd_rn(b.v[k], r.v[k]);
+    }
+    if (p.bias != nullptr) {
+      Row<VEC> b = ld_row<VEC>(p.bias + col[it]);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) r.v[k] = __fadd_rn(r.v[k], b.v[k]);
+    }
+    st_row<VEC>(p.out + seg * p.ld_out + col[it], r);
+  }
+}
+
+template <int VEC, int G, int ITER, int U>
+static int launch(const SegParams& p, cudaStream_t stream) {
+  constexpr int kGroups = kThreads / G;
+  const int64_t blocks = (p.nseg + kGroups - 1) / kGroups;
+  if (blocks > 0x7fffffffLL) {
+    set_error("segment_reduce: too many segments (%lld)", (long long)p.nseg);
+    return DMP_ERR_UNSUPPORTED;
+  }
+  segment_reduce_kernel<VEC, G, ITER, U><<<(unsigned)blocks, kThreads, 0, stream>>>(p);
+  return launch_status("segment_reduce_kernel");
+}
+
+template <int VEC>
+static int dispatch(const SegParams& p, const Shape& s, cudaStream_t stream) {
+  if (s.g == 8) return launch<VEC, 8, 1, 8>(p, stream);
+  if (s.g == 16) return launch<VEC, 16, 1, 8>(p, stream);
+  if (s.iter == 1) return launch<VEC, 32, 1, 8>(p, stream);
+  if (s.iter == 2) return launch<VEC, 32, 2, 4>(p, stream);
+  return launch<VEC, 32, 4, 2>(p, stream);
+}
+
+}  // namespace dmp
+
+extern "C" int dmp_segment_reduce(const int32_t* indptr, const int32_t* eid, const float* w_perm,
+                                  const float* V, int64_t ldV, int64_t rev_col_offset,
+                                  const float* base, int64_t ld_base, const float* bias,
+                                  float* out, int64_t ld_out, int64_t num_segments, int64_t H, int mode,
+                                  void* stream) {
+  using namespace dmp;
+  DMP_CHECK_ARG(num_segments >= 0 && H >= 0, "segment_reduce: negative size");
+  if (num_segments == 0 || H == 0) return DMP_OK;
+  // eid / V may be NULL only for an edgeless graph (every segment empty: they are never dereferenced)
+  DMP_CHECK_ARG(indptr && out, "segment_reduce: null pointer");
+  DMP_CHECK_ARG(ldV >= H && ld_out >= H && (base == nullptr || ld_base >= H),
+                "segment_reduce: leading dimension smaller than H");
+  const int vec = pick_vec(H, {ldV, ld_out, base ? ld_base : 0, rev_col_offset}, {V, out, base, bias});
+  const int64_t chunk = max_chunk(vec);
+  for (int64_t c0 = 0; c0 < H; c0 += chunk) {
+    const int64_t Hc = (H - c0 < chunk) ? (H - c0) : chunk;
+    SegParams p;
+    p.indptr = indptr;
+    p.eid = reinterpret_cast<const uint32_t*>(eid);
+    p.w_perm = w_perm;
+    p.V = V + c0;
+    p.ldV = ldV;
+    p.rev_off = rev_col_offset;
+    p.base = base ? base + c0 : nullptr;
+    p.ld_base = ld_base;
+    p.bias = bias ? bias + c0 : nullptr;
+    p.out = out + c0;
+    p.ld_out = ld_out;
+    p.nseg = num_segments;
+    p.H = (int)Hc;
+    p.mode = mode;
+    const Shape s = pick_shape(Hc, vec);
+    int rc;
+    if (vec == 4) rc = dispatch<4>(p, s, (cudaStream_t)stream);
+    else if (vec == 2) rc = dispatch<2>(p, s, (cudaStream_t)stream);
+    else rc = dispatch<1>(p, s, (cudaStream_t)stream);
+    if (rc != DMP_OK) return rc;
+  }
+  return DMP_OK;
+}

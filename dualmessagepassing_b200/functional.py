@@ -1,0 +1,190 @@
+"""Autograd functions over the C ABI (include/dmp_b200.h): the DMPNN sparse core.
+
+`sparse_core` is the differentiable unit that replaces the DGL `update_all` + `apply_edges` pair of
+SubgraphCountingMatching/models/dmpnn.py:158-166 once the dense projections are done:
+
+    node_pre = L_n + segsum_dst(sgn * M * norm) + nbias          (dmpnn.py:113-124,92,131-133)
+    edge_pre = S + coef * P + (Q_d[a] - Q_s[b]) + ebias          (dmpnn.py:112-123,142-149)
+
+Backward is the deterministic sorted-segment form: two segment sums of gE
+(keys a and b) and one gather of gN -- no float atomics anywhere.
+"""
+import torch
+
+from . import _lib
+
+
+def _stream(t):
+    return _lib.stream_ptr(t.device)
+
+
+def segment_reduce(indptr, eid, V, H, *, w_perm=None, rev_col_offset=0, base=None, bias=None, mode=0, out=None):
+    """Raw (non-differentiable) call of dmp_segment_reduce. V: [*, ldV] fp32, returns [nseg, H]."""
+    _lib.require_cuda(indptr, eid, V, w_perm, base, bias)
+    V, ldV = _lib.row_major(V)
+    nseg = indptr.numel() - 1
+    if out is None:
+        out = torch.empty((nseg, H), dtype=torch.float32, device=V.device)
+    ld_base = 0
+    if base is not None:
+        base, ld_base = _lib.row_major(base)
+    if bias is not None:
+        bias = bias.contiguous()
+    out_m, ld_out = _lib.row_major(out)
+    assert out_m.data_ptr() == out.data_ptr(), "out must have dense rows"
+    with torch.cuda.device(V.device):
+        _lib.check(_lib.load().dmp_segment_reduce(
+            _lib.ptr(indptr), _lib.ptr(eid), _lib.ptr(w_perm), _lib.ptr(V), ldV, rev_col_offset,
+            _lib.ptr(base), ld_base, _lib.ptr(bias), _lib.ptr(out), ld_out, nseg, H, mode, _stream(V)),
+            "dmp_segment_reduce")
+    return out
+
+
+def edge_update(plan, S, P, Qd, Qs, ebias, order, out=None, edge_agg=None):
+    """Raw call of dmp_edge_update; `out` may be S itself (in place)."""
+    _lib.require_cuda(S, P, Qd, Qs, ebias)
+    S, ldS = _lib.row_major(S)
+    P, ldP = _lib.row_major(P)
+    Qd, ldQd = _lib.row_major(Qd)
+    Qs, ldQs = _lib.row_major(Qs)
+    E, H = S.shape
+    if out is None:
+        out = torch.empty((E, H), dtype=torch.float32, device=S.device)
+    _, ld_out = _lib.row_major(out)
+    ld_agg = 0
+    if edge_agg is not None:
+        _, ld_agg = _lib.row_major(edge_agg)
+    if ebias is not None:
+        ebias = ebias.contiguous()
+    with torch.cuda.device(S.device):
+        _lib.check(_lib.load().dmp_edge_update(
+            _lib.ptr(plan.a32), _lib.ptr(plan.b32), _lib.ptr(plan.coef), _lib.ptr(S), ldS, _lib.ptr(P), ldP,
+            _lib.ptr(Qd), ldQd, _lib.ptr(Qs), ldQs, _lib.ptr(ebias), _lib.ptr(out), ld_out,
+            _lib.ptr(edge_agg), ld_agg, E, H, order, _stream(S)), "dmp_edge_update")
+    return out
+
+
+def edge_backward(plan, norm_flat, gN, gE, *, want_T=True, want_CG=True, t_rev_col_offset=0, T=None, CG=None):
+    """Raw call of dmp_edge_backward: T = sgn*gN[dst]*norm (optionally into the rev half), CG = coef*gE."""
+    H = gN.shape[1] if gN is not None else gE.shape[1]
+    dev = gN.device if gN is not None else gE.device
+    ld_gN = ld_gE = ldT = ldCG = 0
+    if want_T:
+        gN, ld_gN = _lib.row_major(gN)
+        if T is None:
+            if t_rev_col_offset:
+                T = torch.zeros((plan.E, t_rev_col_offset + H), dtype=torch.float32, device=dev)
+            else:
+                T = torch.empty((plan.E, H), dtype=torch.float32, device=dev)
+        _, ldT = _lib.row_major(T)
+    if want_CG:
+        gE, ld_gE = _lib.row_major(gE)
+        if CG is None:
+            CG = torch.empty((plan.E, H), dtype=torch.float32, device=dev)
+        _, ldCG = _lib.row_major(CG)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().dmp_edge_backward(
+            _lib.ptr(plan.dst32), _lib.ptr(plan.rev), _lib.ptr(norm_flat), _lib.ptr(plan.coef),
+            _lib.ptr(gN if want_T else None), ld_gN, _lib.ptr(gE if want_CG else None), ld_gE,
+            _lib.ptr(T if want_T else None), ldT, t_rev_col_offset, _lib.ptr(CG if want_CG else None), ldCG,
+            plan.E, H, _lib.stream_ptr(dev)), "dmp_edge_backward")
+    return (T if want_T else None), (CG if want_CG else None)
+
+
+class _SparseCore(torch.autograd.Function):
+    """node_pre, edge_pre = f(M, S, P, L_n, Q_d, Q_s, nbias, ebias)."""
+
+    @staticmethod
+    def forward(ctx, plan, norm, order, m_rev_off, M, S, P, Ln, Qd, Qs, nbias, ebias):
+        H = S.shape[1]
+        norm_flat = norm_perm = None
+        if norm is not None:
+            norm_flat, norm_perm = plan.norm_permuted(norm)
+        node_pre = segment_reduce(plan.csc_indptr, plan.csc_eid, M, H, w_perm=norm_perm,
+                                  rev_col_offset=m_rev_off, base=Ln, bias=nbias, mode=_lib.SEG_SIGN_BY_REV)
+        edge_pre = edge_update(plan, S, P, Qd, Qs, ebias, order)
+        ctx.plan, ctx.norm_flat, ctx.m_rev_off, ctx.H = plan, norm_flat, m_rev_off, H
+        ctx.m_cols = M.shape[1]
+        ctx.has_bias = (nbias is not None, ebias is not None)
+        return node_pre, edge_pre
+
+    @staticmethod
+    def backward(ctx, gN, gE):
+        plan, H = ctx.plan, ctx.H
+        need = ctx.needs_input_grad  # (plan, norm, order, m_rev_off, M, S, P, Ln, Qd, Qs, nbias, ebias)
+        gN = gN.contiguous()
+        gE = gE.contiguous()
+        dM = dP = dQd = dQs = dnb = deb = None
+        if need[4] or need[6]:
+            T = None
+            if need[4] and ctx.m_rev_off:
+                T = torch.zeros((plan.E, ctx.m_cols), dtype=torch.float32, device=gE.device)
+            dM, dP = edge_backward(plan, ctx.norm_flat, gN, gE, want_T=need[4], want_CG=need[6],
+                                   t_rev_col_offset=ctx.m_rev_off, T=T)
+        if need[8]:
+            dQd = segment_reduce(plan.a_indptr, plan.a_eid, gE, H)
+        if need[9]:
+            dQs = segment_reduce(plan.b_indptr, plan.b_eid, gE, H, mode=_lib.SEG_NEGATE_OUT)
+        if ctx.has_bias[0] and need[10]:
+            dnb = gN.sum(0)
+        if ctx.has_bias[1] and need[11]:
+            deb = gE.sum(0)
+        return (None, None, None, None, dM, gE if need[5] else None, dP, gN if need[7] else None,
+                dQd, dQs, dnb, deb)
+
+
+def sparse_core(plan, M, S, P, Ln, Qd, Qs, nbias=None, ebias=None, *, norm=None, order=_lib.ORDER_SCM,
+                m_rev_off=0):
+    _lib.require_cuda(M, S, P, Ln, Qd, Qs)
+    return _SparseCore.apply(plan, norm, order, m_rev_off, M, S, P, Ln, Qd, Qs, nbias, ebias)
+
+
+_ACT_IDS = {"none": _lib.ACT_NONE, "relu": _lib.ACT_RELU, "leaky_relu": _lib.ACT_LEAKY_RELU,
+            "tanh": _lib.ACT_TANH, "sigmoid": _lib.ACT_SIGMOID}
+
+
+class _GateResidual(torch.autograd.Function):
+    """out = prev + gate * act(x)   (row A7: dmpnn.py:236-241,266-275; act only for MLP-less layers)."""
+
+    @staticmethod
+    def forward(ctx, x, gate, prev, act, slope):
+        _lib.require_cuda(x, gate, prev)
+        x, ldx = _lib.row_major(x)
+        rows, H = x.shape
+        out = torch.empty_like(x)
+        ld_prev = 0
+        if prev is not None:
+            prev, ld_prev = _lib.row_major(prev)
+        g = None
+        if gate is not None:
+            g = gate.reshape(-1).contiguous().float()
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().dmp_gate_residual(_lib.ptr(x), ldx, _lib.ptr(g), _lib.ptr(prev), ld_prev,
+                                                     _lib.ptr(out), H, rows, H, act, slope, _stream(x)),
+                       "dmp_gate_residual")
+        ctx.save_for_backward(x if act != _lib.ACT_NONE else None, g)
+        ctx.act, ctx.slope, ctx.has_prev = act, slope, prev is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, g = ctx.saved_tensors
+        gout, ldg = _lib.row_major(gout.contiguous())
+        rows, H = gout.shape
+        gx = None
+        if ctx.needs_input_grad[0]:
+            if g is None and ctx.act == _lib.ACT_NONE:
+                gx = gout
+            else:
+                gx = torch.empty_like(gout)
+                with torch.cuda.device(gout.device):
+                    _lib.check(_lib.load().dmp_gate_residual_backward(
+                        _lib.ptr(gout), ldg, _lib.ptr(x), H, _lib.ptr(g), _lib.ptr(gx), H, rows, H, ctx.act,
+                        ctx.slope, _stream(gout)), "dmp_gate_residual_backward")
+        gprev = gout if (ctx.has_prev and ctx.needs_input_grad[2]) else None
+        return gx, None, gprev, None, None
+
+
+def gate_residual(x, gate=None, prev=None, act="none", slope=0.0):
+    """Fused `prev + gate * act(x)`; gate is [rows] or [rows,1] (0/1 mask or soft gate), no grad to it."""
+    return _GateResidual.apply(x, gate, prev, _ACT_IDS[act], float(slope))

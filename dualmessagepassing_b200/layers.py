@@ -1,0 +1,249 @@
+"""Drop-in DMPNN layers: same constructors, parameter names and call signatures as the reference.
+
+  DMPLayer        <- SubgraphCountingMatching/models/dmpnn.py:16-176
+  DualGraphConv   <- UnsupervisedNodeClassification/Model/DMPNN/src/model.py:117-280
+
+`forward(graph, node_feat, edge_feat[, edge_norm])` takes a (batched) DGLGraph or a `DMPGraph` whose
+tensors live on a CUDA device.  The DGL `update_all` / `apply_edges` path is replaced by the sm_100a
+sparse core behind the C ABI (`functional.sparse_core`); the per-layer projections stay dense GEMMs
+(cuBLAS through torch.mm).  Node-side projections are done BEFORE the endpoint gather
+(`Q = X_v W`, then `Q[a] - Q[b]`), which is bit-identical per row to the reference's gather-then-project
+ and removes E-sized GEMMs; only the selected branch of the reversed / forward
+message is computed instead of both followed by masked_fill.
+
+There is no CPU path: CPU tensors raise.
+"""
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .act import map_activation_str_to_layer
+from .constants import (EDGEFEAT, LEAKY_RELU_A, NODEFEAT, OUTDEGREE, REVFLAG, UNC_FEAT, UNC_NORM,
+                        UNC_OUTDEGREE, UNC_REVFLAG)
+from .functional import sparse_core
+from .init import init_module, init_weight
+from .plan import get_plan
+
+
+class _SplitMM(torch.autograd.Function):
+    """M[:h] = X[:h] @ W0 ; M[h:] = X[h:] @ W1 written into one buffer (the [forward | reversed] edge layout
+    produced by add_reversed_edges on a single graph): each edge only pays for its own branch."""
+
+    @staticmethod
+    def forward(ctx, X, W0, W1, h):
+        M = torch.empty((X.shape[0], W0.shape[1]), dtype=X.dtype, device=X.device)
+        torch.mm(X[:h], W0, out=M[:h])
+        torch.mm(X[h:], W1, out=M[h:])
+        ctx.save_for_backward(X, W0, W1)
+        ctx.h = h
+        return M
+
+    @staticmethod
+    def backward(ctx, gM):
+        X, W0, W1 = ctx.saved_tensors
+        h = ctx.h
+        gX = gW0 = gW1 = None
+        if ctx.needs_input_grad[0]:
+            gX = torch.empty_like(X)
+            torch.mm(gM[:h], W0.t(), out=gX[:h])
+            torch.mm(gM[h:], W1.t(), out=gX[h:])
+        if ctx.needs_input_grad[1]:
+            gW0 = X[:h].t() @ gM[:h]
+        if ctx.needs_input_grad[2]:
+            gW1 = X[h:].t() @ gM[h:]
+        return gX, gW0, gW1, None
+
+
+def dual_message_passing(plan, node_feat, edge_feat, in_weight, out_weight, src_weight, dst_weight,
+                         nloop_weight, eloop_weight, nbias, ebias, norm=None, order=_lib.ORDER_SCM):
+    """(node_pre, edge_pre) of one dual message-passing step: the part of the reference layer between the
+    frame initialisation and the MLP/activation (dmpnn.py:111-133,142-149)."""
+    _lib.require_cuda(node_feat, edge_feat)
+    if node_feat.shape[0] != plan.N or edge_feat.shape[0] != plan.E:
+        raise ValueError("feature rows (%d nodes, %d edges) do not match the graph (%d, %d)"
+                         % (node_feat.shape[0], edge_feat.shape[0], plan.N, plan.E))
+    X_v = node_feat.float()
+    X_e = edge_feat.float()
+    H = nloop_weight.shape[1]
+    # node-sized projections (project-then-gather)
+    Ln = X_v @ nloop_weight
+    Qd = X_v @ dst_weight
+    Qs = X_v @ src_weight
+    # edge-sized projections
+    S = X_e @ eloop_weight
+    P = X_e @ (src_weight - dst_weight)
+    m_rev_off = 0
+    if plan.rev_layout == "none":
+        M = X_e @ in_weight
+    elif plan.rev_layout == "halves":
+        M = _SplitMM.apply(X_e, in_weight, out_weight, plan.E // 2)
+    else:
+        M = X_e @ torch.cat([in_weight, out_weight], dim=1)  # [E, 2H]: branch picked inside the kernel
+        m_rev_off = H
+    return sparse_core(plan, M, S, P, Ln, Qd, Qs, nbias, ebias, norm=norm, order=order, m_rev_off=m_rev_off)
+
+
+class DMPLayer(nn.Module):
+    """SubgraphCountingMatching/models/dmpnn.py:16-176 -- same constructor, state_dict and forward."""
+
+    def __init__(self, input_dim, hidden_dim, init_neigenv=4.0, init_eeigenv=4.0, bias=True,
+                 num_mlp_layers=2, batch_norm=True, act_func="relu", dropout=0.0):
+        super().__init__()
+        self.input_dim = input_dim
+        self.hidden_dim = hidden_dim
+        self.act_func = act_func
+
+        def weight():
+            return nn.Parameter(torch.empty(input_dim, hidden_dim))
+
+        self.in_weight = weight()
+        self.out_weight = weight()
+        self.src_weight = weight()
+        self.dst_weight = weight()
+        self.nloop_weight = weight()
+        self.eloop_weight = weight()
+        if bias:
+            self.nbias = nn.Parameter(torch.empty(hidden_dim))
+            self.ebias = nn.Parameter(torch.empty(hidden_dim))
+        else:
+            self.register_parameter("nbias", None)
+            self.register_parameter("ebias", None)
+
+        def mlp():
+            mods = []
+            for i in range(num_mlp_layers):
+                mods.append(nn.Linear(hidden_dim, hidden_dim))
+                if i != num_mlp_layers - 1:
+                    if batch_norm:
+                        mods.append(nn.BatchNorm1d(hidden_dim))
+                    mods.append(map_activation_str_to_layer(act_func))
+            return nn.Sequential(*mods)
+
+        self.nmlp = mlp()
+        self.emlp = mlp()
+        self.act = map_activation_str_to_layer(act_func)
+        self.drop = nn.Dropout(dropout)
+
+        # same RNG consumption order as the reference (dmpnn.py:64-77): six weights, then the MLPs
+        for w in (self.in_weight, self.out_weight, self.src_weight, self.dst_weight, self.nloop_weight,
+                  self.eloop_weight):
+            init_weight(w, activation=act_func, init="uniform")
+        for m in self.nmlp.modules():
+            init_module(m, activation=act_func, init="uniform")
+        for m in self.emlp.modules():
+            init_module(m, activation=act_func, init="uniform")
+        if bias:
+            nn.init.zeros_(self.nbias)
+            nn.init.zeros_(self.ebias)
+        with torch.no_grad():  # "reparametrisation trick" dmpnn.py:79-86
+            self.in_weight.div_(init_neigenv)
+            self.out_weight.div_(init_neigenv)
+            self.nloop_weight.div_(init_neigenv)
+            self.src_weight.div_(init_eeigenv)
+            self.dst_weight.div_(init_eeigenv)
+            self.eloop_weight.div_(init_eeigenv)
+
+    def forward(self, graph, node_feat, edge_feat):
+        plan = get_plan(graph, REVFLAG, OUTDEGREE)
+        # frame side effects of dmpnn.py:96-109 (inputs stay bound to the graph)
+        graph.ndata[NODEFEAT] = node_feat
+        graph.edata[EDGEFEAT] = edge_feat
+        node_pre, edge_pre = dual_message_passing(
+            plan, node_feat, edge_feat, self.in_weight, self.out_weight, self.src_weight, self.dst_weight,
+            self.nloop_weight, self.eloop_weight, self.nbias, self.ebias, order=_lib.ORDER_SCM)
+        if len(self.nmlp) > 0:
+            node_out = self.nmlp(node_pre)
+        else:
+            node_out = self.act(node_pre)
+        if len(self.emlp) > 0:
+            edge_out = self.emlp(edge_pre)
+        else:
+            edge_out = self.act(edge_pre)
+        return self.drop(node_out), self.drop(edge_out)
+
+    def extra_repr(self):
+        return "in=%s, out=%s" % (self.input_dim, self.hidden_dim)
+
+    def get_output_dim(self):
+        return self.hidden_dim
+
+
+class DualGraphConv(nn.Module):
+    """UnsupervisedNodeClassification/Model/DMPNN/src/model.py:117-280 -- same constructor, state_dict
+    (including the unused `nfc` / `efc`, model.py:137-138) and forward(graph, node_feat, edge_feat, edge_norm)."""
+
+    def __init__(self, input_dim, hidden_dim, init_neigenv=4.0, init_eeigenv=4.0, bias=True, batch_norm=True,
+                 activation=None, dropout=0.0):
+        super().__init__()
+        self.input_dim = input_dim
+        self.hidden_dim = hidden_dim
+
+        def weight():
+            return nn.Parameter(torch.empty(input_dim, hidden_dim))
+
+        self.in_weight = weight()
+        self.out_weight = weight()
+        self.src_weight = weight()
+        self.dst_weight = weight()
+        self.nloop_weight = weight()
+        self.eloop_weight = weight()
+        self.nfc = nn.Linear(hidden_dim, hidden_dim)
+        self.efc = nn.Linear(hidden_dim, hidden_dim)
+        if bias:
+            self.nbias = nn.Parameter(torch.zeros(hidden_dim))
+            self.ebias = nn.Parameter(torch.zeros(hidden_dim))
+        else:
+            self.register_parameter("nbias", None)
+            self.register_parameter("ebias", None)
+
+        def mlp():
+            mods = [nn.Linear(hidden_dim, hidden_dim)]
+            if batch_norm:
+                mods.append(nn.BatchNorm1d(hidden_dim))
+            mods.append(nn.LeakyReLU(LEAKY_RELU_A) if activation is None else activation)
+            mods.append(nn.Linear(hidden_dim, hidden_dim))
+            return nn.Sequential(*mods)
+
+        self.nmlp = mlp()
+        self.emlp = mlp()
+        self.act = activation
+        self.drop = nn.Dropout(dropout)
+
+        for w in (self.in_weight, self.out_weight, self.src_weight, self.dst_weight, self.nloop_weight,
+                  self.eloop_weight, self.nmlp[0].weight, self.nmlp[-1].weight, self.emlp[0].weight,
+                  self.emlp[-1].weight):
+            nn.init.xavier_uniform_(w)
+        for b in (self.nmlp[0].bias, self.nmlp[-1].bias, self.emlp[0].bias, self.emlp[-1].bias):
+            nn.init.zeros_(b)
+        with torch.no_grad():
+            self.in_weight.div_(init_neigenv)
+            self.out_weight.div_(init_neigenv)
+            self.nloop_weight.div_(init_neigenv)
+            self.src_weight.div_(init_eeigenv)
+            self.dst_weight.div_(init_eeigenv)
+            self.eloop_weight.div_(init_eeigenv)
+
+    def forward(self, graph, node_feat, edge_feat, edge_norm=None):
+        plan = get_plan(graph, UNC_REVFLAG, UNC_OUTDEGREE)
+        graph.ndata[UNC_FEAT] = node_feat
+        graph.edata[UNC_FEAT] = edge_feat
+        if edge_norm is not None:
+            graph.edata[UNC_NORM] = edge_norm
+        norm = graph.edata[UNC_NORM] if UNC_NORM in graph.edata else None  # model.py:234: key presence decides
+        node_pre, edge_pre = dual_message_passing(
+            plan, node_feat, edge_feat, self.in_weight, self.out_weight, self.src_weight, self.dst_weight,
+            self.nloop_weight, self.eloop_weight, self.nbias, self.ebias, norm=norm, order=_lib.ORDER_UNC)
+        # model.py:245,260: the reference calls self.drop(out) and discards the result -- a numerical
+        # no-op that only advances the RNG in training mode; mirrored for RNG-stream parity.
+        if self.training and self.drop.p > 0:
+            self.drop(node_pre)
+            self.drop(edge_pre)
+        node_out = self.nmlp(node_pre)
+        edge_out = self.emlp(edge_pre)
+        if self.act:
+            node_out = self.act(node_out)
+            edge_out = self.act(edge_out)
+        return node_out, edge_out
+
+    def extra_repr(self):
+        return "in=%s, out=%s" % (self.input_dim, self.hidden_dim)

@@ -1,0 +1,161 @@
+/* dmp_b200.h -- C ABI of libdmp_b200.so: the sparse core of the DMPNN dual message-passing layer,
+ * hand-written CUDA for sm_100a (B200).
+ *
+ * The reference (HKUST-KnowComp/DualMessagePassing) has no FFI: its boundary is the Python module
+ * `DMPLayer.forward(graph, node_feat, edge_feat)` (SubgraphCountingMatching/models/dmpnn.py:158-166)
+ * and `DualGraphConv.forward(graph, node_feat, edge_feat, edge_norm)`
+ * (UnsupervisedNodeClassification/Model/DMPNN/src/model.py:267-273), which reach native code only
+ * through DGL (`update_all` / `apply_edges` / `fn.sum`) and ATen.  The entry points below are what a
+ * binding for that path would call instead of DGL; each one cites the reference lines it replaces.
+ * INTEGRATION.md shows the ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the parameter name ends in `_host`;
+ *   - sizes are int64_t, indices handed in by the caller are int64 (DGL's id type), indices the
+ *     library produces are int32 (E and N must be < 2^31);
+ *   - feature matrices are row-major fp32 with an explicit leading dimension `ld*` (in floats);
+ *   - `stream` is a cudaStream_t passed as void*; nothing synchronises, nothing allocates;
+ *   - return value: 0 = ok, negative = error, message via dmp_last_error() (thread-local);
+ *   - all floating-point reductions run in a fixed order (ascending edge id inside a segment,
+ *     round-to-nearest adds/multiplies, no FMA contraction, no atomics): results are bit-reproducible
+ *     and equal to a sequential CPU loop in edge-id order.
+ */
+#ifndef DMP_B200_H_
+#define DMP_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define DMP_API __attribute__((visibility("default")))
+#else
+#define DMP_API
+#endif
+
+#define DMP_OK 0
+#define DMP_ERR_INVALID (-1)
+#define DMP_ERR_CUDA (-2)
+#define DMP_ERR_UNSUPPORTED (-3)
+
+/* bit 31 of an entry of a segment's edge-id list carries the edge's reversed flag */
+#define DMP_EID_MASK 0x7fffffff
+#define DMP_REV_BIT 0x80000000u
+
+/* dmp_segment_reduce mode bits */
+#define DMP_SEG_SIGN_BY_REV 1 /* message sign: -1 on forward edges, +1 on reversed edges (dmpnn.py:113,121) */
+#define DMP_SEG_NEGATE_OUT 2  /* out = -(sum)  (used for dQ_s = -SB in backward)                         */
+
+/* dmp_edge_update order */
+#define DMP_ORDER_SCM 0 /* ((eloop + add) + agg) + ebias   dmpnn.py:147-149  */
+#define DMP_ORDER_UNC 1 /* ((eloop + agg) + add) + ebias   model.py:257-259  */
+
+/* activation ids for the fused epilogues (dmpnn.py:138,154 when num_mlp_layers == 0) */
+#define DMP_ACT_NONE 0
+#define DMP_ACT_RELU 1
+#define DMP_ACT_LEAKY_RELU 2 /* slope passed explicitly (reference: 1/5.5, constants.py:10) */
+#define DMP_ACT_TANH 3
+#define DMP_ACT_SIGMOID 4
+
+DMP_API const char* dmp_last_error(void);
+DMP_API int dmp_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Graph plan (row A0): replaces DGL's COO->CSC conversion behind `fn.sum` (dmpnn.py:92,163),
+ * `graph.out_degrees()` (dmpnn.py:100-101), the per-edge endpoint gathers' index set-up
+ * (`edges.src/dst`, dmpnn.py:112,120) and the degree term of dmpnn.py:144-146.
+ *
+ *   src,dst   int64 [E]   COO in edge-id order          rev      uint8 [E] or NULL (is_reversed flag)
+ *   out_deg   int64 [N] or NULL (NULL => computed as bincount(src), written to out_deg_out)
+ *   coef_lut  fp32 [lut_len] or NULL: coef_lut[d] = 2*(1+log2(1+d)) precomputed by the host maths
+ *             library so that small degrees are bit-identical to the reference's CPU log2; degrees
+ *             >= lut_len use the device log2f.
+ * outputs (caller-allocated):
+ *   dst32,a32,b32 int32 [E]: destination; endpoint meeting W_dst (a = rev ? src : dst); endpoint
+ *             meeting W_src (b = rev ? dst : src)
+ *   csc_indptr/a_indptr/b_indptr int32 [N+1]; csc_eid/a_eid/b_eid int32 [E]: stable counting sort
+ *             of edge ids by dst / a / b (ascending edge id inside a segment), bit 31 = rev flag
+ *   out_deg_out int64 [N]; coef fp32 [E] = 2*(1+log2(1+out_deg[dst[e]]))
+ *   status    int32 [1]: set non-zero on device if an endpoint is outside [0,N)
+ *   ws        workspace of at least dmp_plan_workspace_bytes(N,E) bytes
+ * If rev == NULL the a-structure equals the CSC and the b-structure is the CSR; they are still
+ * written so that callers need no special case.
+ */
+DMP_API int dmp_plan_workspace_bytes(int64_t num_nodes, int64_t num_edges, int64_t* bytes_host);
+DMP_API int dmp_plan_build(const int64_t* src, const int64_t* dst, const uint8_t* rev, const int64_t* out_deg,
+                   int64_t num_nodes, int64_t num_edges, const float* coef_lut, int64_t lut_len,
+                   int32_t* dst32, int32_t* a32, int32_t* b32,
+                   int32_t* csc_indptr, int32_t* csc_eid, int32_t* a_indptr, int32_t* a_eid,
+                   int32_t* b_indptr, int32_t* b_eid, int64_t* out_deg_out, float* coef,
+                   int32_t* status, void* ws, int64_t ws_bytes, void* stream);
+
+/* out[j] = values[eid[j] & DMP_EID_MASK]  (per-segment-position copy of a per-edge scalar, e.g. the
+ * UNC `norm`, model.py:234-235), so the reduce kernel streams it instead of gathering it. */
+DMP_API int dmp_permute_edge_scalar(const int32_t* eid, const float* values, float* out, int64_t num_edges,
+                            void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Segment reduce (rows A3 + A4 bias part; backward: autograd index_add_ of the endpoint gathers):
+ *
+ *   out[x,:] = ((base[x,:] + sum_{j in [indptr[x], indptr[x+1])} w_j * sgn_j * V[e_j, off_j : off_j+H]) + bias)
+ *
+ * with e_j = eid[j] & DMP_EID_MASK, r_j = eid[j] >> 31, sgn_j = (mode & SIGN_BY_REV) ? (r_j ? +1 : -1) : +1,
+ * off_j = r_j ? rev_col_offset : 0, w_j = w_perm ? w_perm[j] : 1 (applied as a separate rounding, like
+ * `node_msg * norm`), accumulated sequentially from 0.0f in ascending j.  base/bias/w_perm may be NULL.
+ * Replaces `fn.sum(node_msg -> node_agg)` + `matmul(nloop) + agg + nbias` (dmpnn.py:92,131-133) and, in
+ * backward, the scatter-adds of d(edge_msg) onto the endpoint rows.
+ */
+DMP_API int dmp_segment_reduce(const int32_t* indptr, const int32_t* eid, const float* w_perm,
+                       const float* V, int64_t ldV, int64_t rev_col_offset,
+                       const float* base, int64_t ld_base, const float* bias,
+                       float* out, int64_t ld_out, int64_t num_segments, int64_t H, int mode,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Edge update (rows A2 edge_msg + A5): per edge e
+ *   msg = Qd[a32[e],:] - Qs[b32[e],:]                      (dmpnn.py:112,120,123)
+ *   add = coef[e] * P[e,:]                                  (dmpnn.py:146)
+ *   out[e,:] = ((S[e,:] + add) + msg) + ebias   (SCM)   or  ((S[e,:] + msg) + add) + ebias   (UNC)
+ * S = X_e*W_eloop, P = X_e*(W_src-W_dst), Qd = X_v*W_dst, Qs = X_v*W_src are produced by the dense
+ * stage.  edge_agg (optional, may be NULL) receives msg, mirroring the reference's frame side effect
+ * `edata["edge_agg"]` (dmpnn.py:126).  out may alias S.
+ */
+DMP_API int dmp_edge_update(const int32_t* a32, const int32_t* b32, const float* coef,
+                    const float* S, int64_t ldS, const float* P, int64_t ldP,
+                    const float* Qd, int64_t ldQd, const float* Qs, int64_t ldQs, const float* ebias,
+                    float* out, int64_t ld_out, float* edge_agg, int64_t ld_agg,
+                    int64_t num_edges, int64_t H, int order, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Backward edge-side gather (gSpMM backward of `fn.sum` + derivative of the degree term):
+ *   T[e, off_e : off_e+H] = sgn_e * gN[dst32[e],:] (* norm[e])   sgn_e = rev[e] ? +1 : -1   (d node_msg)
+ *   CG[e,:] = coef[e] * gE[e,:]                            (d P)          -- skipped if CG == NULL
+ * off_e = rev[e] ? T_rev_col_offset : 0 (mirror of dmp_segment_reduce's rev_col_offset: with the
+ * two-branch [E,2H] message buffer the gradient lands in the half the edge's branch read from).
+ * rev may be NULL (all forward), norm may be NULL.  T may be NULL to produce CG only.
+ */
+DMP_API int dmp_edge_backward(const int32_t* dst32, const uint8_t* rev, const float* norm, const float* coef,
+                      const float* gN, int64_t ld_gN, const float* gE, int64_t ld_gE,
+                      float* T, int64_t ldT, int64_t T_rev_col_offset, float* CG, int64_t ldCG,
+                      int64_t num_edges, int64_t H, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused elementwise epilogue of the rep-net loop (row A7, dmpnn.py:236-241,266-275):
+ *   y = act(x)            (act only when the layer has no MLP, dmpnn.py:138,154)
+ *   y = y * gate[row]     (gate [rows] or NULL; pattern-side masked_fill is the 0/1 gate)
+ *   out = prev + y        (prev NULL => no residual)
+ * and its backward: gx = gout * gate[row] * act'(x).
+ */
+DMP_API int dmp_gate_residual(const float* x, int64_t ldx, const float* gate, const float* prev, int64_t ld_prev,
+                      float* out, int64_t ld_out, int64_t rows, int64_t H, int act, float slope,
+                      void* stream);
+DMP_API int dmp_gate_residual_backward(const float* gout, int64_t ld_gout, const float* x, int64_t ldx,
+                               const float* gate, float* gx, int64_t ld_gx, int64_t rows, int64_t H,
+                               int act, float slope, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMP_B200_H_ */

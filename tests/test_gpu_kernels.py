@@ -1,0 +1,179 @@
+"""Sparse-core kernels through the C ABI: fp32 BIT-EXACT against the sequential C oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import graph_oracle as go
+from oracle import sparse_core as sc
+from tests._cases import hub_graph, make_graph, t
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [  # (n, e0, H) -- H covers every (VEC, G, ITER) dispatch: 4..512+, odd, 50 (UNC run.sh), 64/128
+    (30, 100, 4), (30, 100, 7), (50, 300, 32), (64, 500, 50), (200, 2000, 64), (300, 3000, 128),
+    (40, 200, 130), (40, 200, 256), (20, 100, 516), (20, 60, 1030),
+]
+
+
+def _plan(s, d, n, r):
+    from dualmessagepassing_b200.plan import DMPPlan
+    return DMPPlan(t(s), t(d), n, rev=t(None if r is None else r.astype(np.uint8)))
+
+
+def _cpu_plan(plan):
+    return {k: getattr(plan, k).cpu() for k in ("dst32", "a32", "b32", "csc_indptr", "csc_eid", "a_indptr", "a_eid",
+                                                "b_indptr", "b_eid", "coef")}
+
+
+@pytest.mark.parametrize("n,e0,H", SHAPES)
+@pytest.mark.parametrize("rev", ["halves", "shuffled", None])
+def test_segment_reduce_bit_exact(n, e0, H, rev):
+    from dualmessagepassing_b200 import _lib, functional as F
+    s, d, r = make_graph(seed=n + H, n=n, e0=e0, rev=rev)
+    plan = _plan(s, d, n, r)
+    cp = _cpu_plan(plan)
+    E = len(s)
+    g = torch.Generator().manual_seed(H)
+    two_branch = rev == "shuffled"
+    M = torch.randn(E, 2 * H if two_branch else H, generator=g)
+    base, bias, norm = torch.randn(n, H, generator=g), torch.randn(H, generator=g), torch.rand(E, generator=g)
+    off = H if two_branch else 0
+    for use_norm in (False, True):
+        w_perm_cpu = norm[(cp["csc_eid"].long() & 0x7FFFFFFF)] if use_norm else None
+        want = sc.seg_reduce(cp["csc_indptr"], cp["csc_eid"], M, H, w_perm=w_perm_cpu, rev_off=off, base=base,
+                             bias=bias, mode=_lib.SEG_SIGN_BY_REV)
+        w_perm = plan.norm_permuted(norm.cuda())[1] if use_norm else None
+        got = F.segment_reduce(plan.csc_indptr, plan.csc_eid, M.cuda(), H, w_perm=w_perm, rev_col_offset=off,
+                               base=base.cuda(), bias=bias.cuda(), mode=_lib.SEG_SIGN_BY_REV)
+        assert torch.equal(got.cpu(), want)
+    # backward flavour: plain / negated sums over the a- and b-keyed segments
+    gE = torch.randn(E, H, generator=g)
+    for ip, ei, mode in (("a_indptr", "a_eid", 0), ("b_indptr", "b_eid", _lib.SEG_NEGATE_OUT)):
+        want = sc.seg_reduce(cp[ip], cp[ei], gE, H, mode=mode)
+        got = F.segment_reduce(getattr(plan, ip), getattr(plan, ei), gE.cuda(), H, mode=mode)
+        assert torch.equal(got.cpu(), want)
+
+
+@pytest.mark.parametrize("n,e0,H", SHAPES)
+@pytest.mark.parametrize("order", [0, 1])
+def test_edge_update_bit_exact(n, e0, H, order):
+    from dualmessagepassing_b200 import functional as F
+    s, d, r = make_graph(seed=7 * n + H, n=n, e0=e0, rev="shuffled")
+    plan = _plan(s, d, n, r)
+    cp = _cpu_plan(plan)
+    E = len(s)
+    g = torch.Generator().manual_seed(H + order)
+    S, P = torch.randn(E, H, generator=g), torch.randn(E, H, generator=g)
+    Qd, Qs, eb = torch.randn(n, H, generator=g), torch.randn(n, H, generator=g), torch.randn(H, generator=g)
+    want, want_agg = sc.edge_update(cp["a32"], cp["b32"], cp["coef"], S, P, Qd, Qs, eb, order, want_agg=True)
+    agg = torch.empty(E, H, device="cuda")
+    got = F.edge_update(plan, S.cuda(), P.cuda(), Qd.cuda(), Qs.cuda(), eb.cuda(), order, edge_agg=agg)
+    assert torch.equal(got.cpu(), want) and torch.equal(agg.cpu(), want_agg)
+    # in place over S, no bias
+    Sg = S.cuda()
+    out = F.edge_update(plan, Sg, P.cuda(), Qd.cuda(), Qs.cuda(), None, order, out=Sg)
+    assert out.data_ptr() == Sg.data_ptr()
+    assert torch.equal(Sg.cpu(), sc.edge_update(cp["a32"], cp["b32"], cp["coef"], S, P, Qd, Qs, None, order))
+
+
+@pytest.mark.parametrize("n,e0,H", SHAPES[:8])
+def test_edge_backward_bit_exact(n, e0, H):
+    from dualmessagepassing_b200 import functional as F
+    s, d, r = make_graph(seed=11 * n + H, n=n, e0=e0, rev="shuffled")
+    plan = _plan(s, d, n, r)
+    cp = _cpu_plan(plan)
+    E = len(s)
+    g = torch.Generator().manual_seed(H)
+    gN, gE, norm = torch.randn(n, H, generator=g), torch.randn(E, H, generator=g), torch.rand(E, generator=g)
+    r8 = torch.from_numpy(r.astype(np.uint8))
+    for nm in (None, norm):
+        for off in (0, H):
+            wT, wCG = sc.edge_backward(cp["dst32"], r8, nm, cp["coef"], gN, gE, t_rev_off=off)
+            T, CG = F.edge_backward(plan, None if nm is None else nm.cuda(), gN.cuda(), gE.cuda(),
+                                    t_rev_col_offset=off)
+            assert torch.equal(T.cpu(), wT) and torch.equal(CG.cpu(), wCG)
+
+
+def test_long_segment_hub_bit_exact_and_deterministic():
+    from dualmessagepassing_b200 import _lib, functional as F
+    s, d, r = hub_graph(21, 400, 2000, 20000)
+    plan = _plan(s, d, 400, r)
+    cp = _cpu_plan(plan)
+    E, H = len(s), 128
+    M = torch.randn(E, H, generator=torch.Generator().manual_seed(3))
+    want = sc.seg_reduce(cp["csc_indptr"], cp["csc_eid"], M, H, mode=_lib.SEG_SIGN_BY_REV)
+    Mg = M.cuda()
+    outs = [F.segment_reduce(plan.csc_indptr, plan.csc_eid, Mg, H, mode=_lib.SEG_SIGN_BY_REV) for _ in range(3)]
+    assert torch.equal(outs[0].cpu(), want)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])  # run-to-run bit stability
+
+
+def test_strided_operands_use_leading_dimension():
+    from dualmessagepassing_b200 import _lib, functional as F
+    s, d, r = make_graph(seed=5, n=40, e0=200, rev="halves")
+    plan = _plan(s, d, 40, r)
+    cp = _cpu_plan(plan)
+    E, H = len(s), 32
+    big = torch.randn(E, 3 * H, generator=torch.Generator().manual_seed(9))
+    view = big[:, H:2 * H]  # ld = 3H, offset H: vector width must fall back correctly if misaligned
+    want = sc.seg_reduce(cp["csc_indptr"], cp["csc_eid"], view.contiguous(), H, mode=_lib.SEG_SIGN_BY_REV)
+    got = F.segment_reduce(plan.csc_indptr, plan.csc_eid, big.cuda()[:, H:2 * H], H, mode=_lib.SEG_SIGN_BY_REV)
+    assert torch.equal(got.cpu(), want)
+    odd = torch.randn(E, H + 1)[:, 1:]  # rows start 4 bytes off 16-byte alignment -> scalar path
+    want = sc.seg_reduce(cp["csc_indptr"], cp["csc_eid"], odd.contiguous(), H)
+    got = F.segment_reduce(plan.csc_indptr, plan.csc_eid, odd.cuda(), H)
+    assert torch.equal(got.cpu(), want)
+
+
+@pytest.mark.parametrize("act,slope", [("none", 0.0), ("relu", 0.0), ("leaky_relu", 1 / 5.5)])
+def test_gate_residual_bit_exact(act, slope):
+    from dualmessagepassing_b200 import functional as F
+    ids = {"none": 0, "relu": 1, "leaky_relu": 2}
+    g = torch.Generator().manual_seed(4)
+    x, prev, gout = torch.randn(333, 64, generator=g), torch.randn(333, 64, generator=g), torch.randn(333, 64, generator=g)
+    gate = (torch.rand(333, generator=g) > 0.4).float()
+    xg = x.cuda().requires_grad_(True)
+    pg = prev.cuda().requires_grad_(True)
+    out = F.gate_residual(xg, gate.cuda(), pg, act=act, slope=slope)
+    assert torch.equal(out.cpu(), sc.gate_residual(x, gate, prev, ids[act], slope))
+    out.backward(gout.cuda())
+    assert torch.equal(xg.grad.cpu(), sc.gate_residual_backward(gout, x, gate, ids[act], slope))
+    assert torch.equal(pg.grad.cpu(), gout)
+
+
+def test_gate_residual_tanh_close():
+    from dualmessagepassing_b200 import functional as F
+    x = torch.randn(100, 50, generator=torch.Generator().manual_seed(5))
+    out = F.gate_residual(x.cuda(), None, None, act="tanh")
+    torch.testing.assert_close(out.cpu(), torch.tanh(x), rtol=1e-6, atol=1e-6)
+
+
+def test_full_size_properties_config5_slice():
+    """Size-independent properties at BASELINE scale (N=2M nodes; E reduced to fit test time is NOT done:
+    this runs the real 40M-edge index build and one reduce): linearity of the segment sum and the
+    checksum identity sum_x out[x] == sum_e sgn_e M[e] in fp64."""
+    from dualmessagepassing_b200 import _lib, functional as F
+    from dualmessagepassing_b200.plan import DMPPlan
+    N, E0, H = 2_000_000, 20_000_000, 32
+    g = torch.Generator(device="cuda").manual_seed(1)
+    u = torch.randint(0, N, (E0,), device="cuda", generator=g)
+    v = torch.randint(0, N, (E0,), device="cuda", generator=g)
+    src, dst = torch.cat([u, v]), torch.cat([v, u])
+    rev = torch.cat([torch.zeros(E0, dtype=torch.uint8, device="cuda"), torch.ones(E0, dtype=torch.uint8, device="cuda")])
+    plan = DMPPlan(src, dst, N, rev=rev)
+    assert plan.rev_layout == "halves"
+    ip = plan.csc_indptr.long()
+    assert int(ip[-1]) == 2 * E0 and bool((ip[1:] >= ip[:-1]).all())
+    assert torch.equal(ip[1:] - ip[:-1], torch.bincount(dst, minlength=N))
+    eid = plan.csc_eid.long() & 0x7FFFFFFF
+    assert torch.equal(torch.sort(eid).values, torch.arange(2 * E0, device="cuda"))  # a permutation
+    assert bool((dst[eid][1:] >= dst[eid][:-1]).all())                                # sorted by destination
+    same = dst[eid][1:] == dst[eid][:-1]
+    assert bool((eid[1:][same] > eid[:-1][same]).all())                               # stable inside a segment
+    M = torch.randn(2 * E0, H, device="cuda", generator=g)
+    out = F.segment_reduce(plan.csc_indptr, plan.csc_eid, M, H, mode=_lib.SEG_SIGN_BY_REV)
+    sgn = rev.double() * 2 - 1
+    want = (M.double() * sgn.unsqueeze(1)).sum(0)
+    torch.testing.assert_close(out.double().sum(0), want, rtol=1e-6, atol=1e-2)
+    out2 = F.segment_reduce(plan.csc_indptr, plan.csc_eid, M * 2, H, mode=_lib.SEG_SIGN_BY_REV)
+    assert torch.equal(out2, out * 2)  # scaling by a power of two commutes with every rounding
