@@ -1,0 +1,421 @@
+#!/usr/bin/env python
+"""bench.py -- DMPNN layer forward+backward throughput on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg5|cfg4|cfg2]
+
+One "step" = one DMPLayer (hidden 128, 2-layer MLPs, leaky_relu; the SubgraphCountingMatching default
+layer) forward + backward over the whole synthetic graph through the module API
+`layer(graph, node_feat, edge_feat)` + `torch.autograd.backward`.  Default workload = BASELINE.json
+configs[4]: one directed Erdos-Renyi graph, 2 M nodes, 20 M edges + 20 M reversed edges, H = 128
+(the configuration the edges/sec metric and the 60 %-of-HBM target are quoted on; it fits one GPU).
+
+  value      edges/s (E counts reversed edges) with everything resident in HBM, CUDA-event timed
+  e2e        same metric with node/edge features starting in pinned HOST memory every step and the
+             step's result (loss scalar + all parameter gradients) read back to the host
+  roofline   dominant hand-written kernel: algorithmic bytes / CUDA-event duration vs measured HBM peak
+  cpu_baseline   the CPU oracle (reference op order, torch CPU, all host threads) on a bounded sample
+
+N > 1: the graph is partitioned by destination-node range (edges live with their destination), node
+states are all-gathered forward and their gradients reduce-scattered backward (parallel.py); value is
+total edges of the whole graph / max-over-ranks step time ("strong" scaling: total work is fixed).
+
+`--impl reference` times the reference's CPU path (oracle restatement, DGL unavailable offline) only.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (nodes, original edges, hidden, description)
+    "cfg5": (2_000_000, 20_000_000, 128,
+             "BASELINE configs[4]: single ER graph 2M nodes / 40M edges (20M + reversed), hidden 128, "
+             "DMPLayer mlp=2 leaky_relu fwd+bwd"),
+    "cfg4": (20_000, 90_000, 128, "BASELINE configs[3]-sized: 20k nodes / 180k edges, hidden 128"),
+    "cfg2": (20_480, 81_920, 64, "BASELINE configs[1] graph side: ~20k nodes / 164k edges, hidden 64"),
+}
+METRIC = "DMPNN layer fwd+bwd edges/sec"
+UNIT = "edges/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS))
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-sample-edges", type=int, default=0, help="override the CPU sample size (edges incl. reversed)")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic graph: directed ER multigraph, numpy PCG64, reversed edges appended
+def make_graph(n, e0, seed):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    u = rng.integers(0, n, size=e0, dtype=np.int64)
+    v = rng.integers(0, n - 1, size=e0, dtype=np.int64)
+    v = v + (v >= u)  # no self loops
+    src = np.concatenate([u, v])
+    dst = np.concatenate([v, u])
+    rev = np.concatenate([np.zeros(e0, np.uint8), np.ones(e0, np.uint8)])
+    return src, dst, rev
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle restatement of the reference layer on host cores
+def cpu_reference_step_fn(n, e0, h, seed):
+    from oracle import dmp_oracle  # the ONLY use of oracle/ in this file: the thing being compared against
+    import dualmessagepassing_b200 as dmp
+    src, dst, rev = make_graph(n, e0, seed)
+    torch.manual_seed(seed)
+    layer = dmp.DMPLayer(h, h, num_mlp_layers=2, batch_norm=False, act_func="leaky_relu")
+    P = {k: v.clone().requires_grad_(True) for k, v in layer.state_dict().items()}
+    E = 2 * e0
+    xv = torch.randn(n, h, requires_grad=True)
+    xe = torch.randn(E, h, requires_grad=True)
+    gv, ge = torch.randn(n, h), torch.randn(E, h)
+    s, d, r = torch.from_numpy(src), torch.from_numpy(dst), torch.from_numpy(rev.astype(bool))
+
+    def step():
+        for t in list(P.values()) + [xv, xe]:
+            t.grad = None
+        nv, ne = dmp_oracle.dmp_layer(P, s, d, n, xv, xe, rev=r, flavour="scm", act_func="leaky_relu")
+        torch.autograd.backward((nv, ne), (gv, ge))
+        return float(nv[0, 0].detach())
+
+    return step, E
+
+
+def cpu_sample_shape(n, e0, budget_s):
+    """Scale the workload down (same average degree) so one CPU step takes about `budget_s` seconds.
+    ~0.13 M edges/s/step was measured for the reference-order restatement on 8 cores."""
+    target_edges = max(100_000, min(2 * e0, int(budget_s * 0.15e6)))
+    scale = target_edges / float(2 * e0)
+    return max(1000, int(n * scale)), max(1000, int(e0 * scale))
+
+
+def run_reference(args):
+    n, e0, h, desc = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    total = args.steps + args.warmup
+    sn, se0 = cpu_sample_shape(n, e0, budget_s=max(2.0, 150.0 / max(total, 1)))
+    if args.cpu_sample_edges:
+        se0 = args.cpu_sample_edges // 2
+        sn = max(1000, int(n * se0 / e0))
+    step, E = cpu_reference_step_fn(sn, se0, h, seed=5000)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    value = E / dt
+    sample = "1/%d-scale %s: %d nodes, %d edges (incl. reversed), H=%d" % (round(2 * e0 / E), args.workload, sn, E, h)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "reference_impl": "oracle/dmp_oracle.py: reference op order on torch CPU "
+                   "(DGL is not installable offline, see DESIGN.md)", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {
+                nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
+            }
+            while not self._stop_evt.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+                time.sleep(0.1)
+        except Exception as exc:  # NVML missing: report that instead of failing the bench
+            self.reasons.add("nvml_unavailable:%s" % type(exc).__name__)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def kernel_bytes(tag, N, E, H, has_norm=False):
+    """Algorithmic bytes of one launch of each hand-written kernel ('Kernels')."""
+    row = 4 * H
+    if tag == "segment_reduce.node_fwd":
+        return E * row + 2 * N * row + 4 * E + 4 * (N + 1) + row + (4 * E if has_norm else 0)
+    if tag.startswith("segment_reduce"):
+        return E * row + N * row + 4 * E + 4 * (N + 1)
+    if tag == "edge_update":
+        return 5 * E * row + 12 * E + row
+    if tag == "edge_backward":
+        return 4 * E * row + 9 * E
+    if tag == "act_inplace":
+        return None  # rows differ (node / edge); filled by caller
+    return None
+
+
+def run_ours(args):
+    import torch.distributed as dist
+
+    import dualmessagepassing_b200 as dmp
+    from dualmessagepassing_b200 import _lib
+    from dualmessagepassing_b200.constants import REVFLAG
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    _lib.load()  # fail loudly if the CUDA extension is missing
+
+    n, e0, h, desc = WORKLOADS[args.workload]
+    E = 2 * e0
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"
+
+    # ---- cpu baseline on rank 0, N=1 only, before the GPU run ------------------------------------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        sn, se0 = cpu_sample_shape(n, e0, budget_s=10.0)
+        step, sE = cpu_reference_step_fn(sn, se0, h, seed=5000)
+        step()
+        t0 = time.perf_counter()
+        step()
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": sE / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": "1/%d-scale %s: %d nodes, %d edges (incl. reversed), H=%d, 1 warm-up + 1 timed "
+                                  "fwd+bwd of oracle/dmp_oracle.py" % (round(E / sE), args.workload, sn, sE, h)}
+        del step
+
+    # ---- build the workload -----------------------------------------------------------------------------
+    src, dst, rev = make_graph(n, e0, seed=5000)
+    torch.manual_seed(5000)
+    layer = dmp.DMPLayer(h, h, num_mlp_layers=2, batch_norm=False, act_func="leaky_relu").to(dev)
+    gen = torch.Generator(device=dev).manual_seed(5000 + rank)
+
+    if world == 1:
+        graph = dmp.DMPGraph(torch.from_numpy(src), torch.from_numpy(dst), n).to(dev)
+        graph.edata[REVFLAG] = torch.from_numpy(rev).to(dev).bool()
+        graph.rev_layout_hint = "halves"
+        runner = None
+        nE, nN = E, n
+    else:
+        from dualmessagepassing_b200.parallel import PartitionedDMPLayer
+        runner = PartitionedDMPLayer(layer, src, dst, rev, n, rank, world, dev)
+        graph = None
+        nE, nN = runner.local_E, runner.local_N
+    del src, dst, rev
+
+    # features, upstream gradients (resident) and their pinned host copies (for the e2e leg)
+    xv = torch.randn(nN, h, device=dev, generator=gen)
+    xe = torch.randn(nE, h, device=dev, generator=gen)
+    gv = torch.randn(nN, h, device=dev, generator=gen)
+    ge = torch.randn(nE, h, device=dev, generator=gen)
+    params = [p for p in layer.parameters()]
+
+    t_plan0 = time.perf_counter()
+    if world == 1:
+        plan = dmp.get_plan(graph, REVFLAG, "out_deg")
+    else:
+        plan = runner.plan
+    torch.cuda.synchronize()
+    plan_ms = (time.perf_counter() - t_plan0) * 1e3
+
+    def step(xv_in, xe_in):
+        for p in params:
+            p.grad = None
+        a = xv_in.requires_grad_(True)
+        b = xe_in.requires_grad_(True)
+        if runner is None:
+            nv, ne = layer(graph, a, b)
+        else:
+            nv, ne = runner(a, b)
+        torch.autograd.backward((nv, ne), (gv, ge))
+        out = (nv, a.grad, b.grad)
+        a.grad = None
+        b.grad = None
+        xv_in.requires_grad_(False)
+        xe_in.requires_grad_(False)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(xv, xe)
+    barrier()
+
+    # ---- timed region: K steps, CUDA events, per-kernel events inside ------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    _lib.PROFILE = []
+    launches0 = _lib.LAUNCHES
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step(xv, xe)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    total_ms = ev0.elapsed_time(ev1)
+    prof, _lib.PROFILE = _lib.PROFILE, None
+    launches = _lib.LAUNCHES - launches0
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    value = E / (ms_per_step * 1e-3)
+
+    # ---- per-kernel durations -> roofline of the dominant hand-written kernel ----------------------------
+    by_tag = {}
+    for tag, e_0, e_1 in prof:
+        by_tag.setdefault(tag, []).append(e_0.elapsed_time(e_1))
+    kernels = {}
+    for tag, ms in by_tag.items():
+        nb = kernel_bytes(tag, nN, nE, h)
+        avg = float(np.mean(ms))
+        entry = {"launches_per_step": len(ms) / args.steps, "avg_ms": avg, "share_of_step": sum(ms) / total_ms}
+        if nb is not None:
+            entry["alg_bytes"] = nb
+            entry["gbs"] = nb / (avg * 1e-3) / 1e9
+            entry["frac"] = entry["gbs"] / hbm_peak
+        kernels[tag] = entry
+    roofline = None
+    cand = {k: v for k, v in kernels.items() if "gbs" in v}
+    if cand:
+        top = max(cand, key=lambda k: cand[k]["avg_ms"] * cand[k]["launches_per_step"])
+        kv = cand[top]
+        roofline = {"kernel": top, "bound": "hbm", "achieved": kv["gbs"], "peak": hbm_peak, "unit": "GB/s",
+                    "frac": kv["frac"], "traffic": None, "alg_bytes_per_launch": kv["alg_bytes"],
+                    "avg_launch_ms": kv["avg_ms"], "peak_source": peak_src}
+        sparse_ms = sum(v["avg_ms"] * v["launches_per_step"] for v in cand.values())
+        sparse_bytes = sum(v["alg_bytes"] * v["launches_per_step"] for v in cand.values())
+        roofline["sparse_core"] = {"ms_per_step": sparse_ms, "alg_bytes_per_step": sparse_bytes,
+                                   "gbs": sparse_bytes / (sparse_ms * 1e-3) / 1e9,
+                                   "frac": sparse_bytes / (sparse_ms * 1e-3) / 1e9 / hbm_peak,
+                                   "edges_per_s": E / (sparse_ms * 1e-3) if world == 1 else None}
+
+    # ---- e2e: features start in pinned host memory every step; loss + parameter grads go back -------------
+    e2e = None
+    if not args.no_e2e:
+        xv_h = torch.empty((nN, h), dtype=torch.float32, pin_memory=True)
+        xe_h = torch.empty((nE, h), dtype=torch.float32, pin_memory=True)
+        xv_h.copy_(xv)
+        xe_h.copy_(xe)
+        n_par = sum(p.numel() for p in params)
+        res_h = torch.empty(n_par + 1, dtype=torch.float32, pin_memory=True)
+
+        def e2e_step():
+            xv.copy_(xv_h, non_blocking=True)
+            xe.copy_(xe_h, non_blocking=True)
+            nv, _, _ = step(xv, xe)
+            flat = torch.cat([nv.sum().reshape(1)] + [p.grad.reshape(-1) for p in params])
+            res_h.copy_(flat, non_blocking=True)
+            torch.cuda.synchronize()
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        barrier()
+        dt = torch.tensor([(time.perf_counter() - t0) / args.e2e_steps], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": E / float(dt.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int((xv_h.numel() + xe_h.numel()) * 4),
+               "d2h_bytes_per_step": int(res_h.numel() * 4), "ms_per_step": float(dt.item()) * 1e3,
+               "steps": args.e2e_steps,
+               "what": "pinned host node/edge features -> HBM, DMPLayer fwd+bwd through the module API, "
+                       "loss scalar + all parameter gradients -> host; graph and its plan stay resident"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "nodes": n, "edges": E, "hidden": h,
+                       "layer": "DMPLayer(128,128,num_mlp_layers=2,batch_norm=False,act_func=leaky_relu)"
+                       if h == 128 else "DMPLayer(h,h,mlp=2,leaky_relu)",
+                       "l2": "inputs larger than L2: each [E,H] fp32 operand is %.1f GB" % (nE * h * 4 / 1e9),
+                       "parallelism": "single GPU" if world == 1 else
+                       "dst-range node partition x%d, all-gather fwd / reduce-scatter bwd" % world,
+                       "plan_build_ms_excluded": plan_ms},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
+            "clocks": clocks, "kernels": kernels,
+            "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) == 0:
+            run_reference(args)
+        return
+    if args.gpus != world and world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run
+        os.execv(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                                  "--nproc-per-node", str(args.gpus), "--master-addr", "127.0.0.1",
+                                  "--master-port", "29531", os.path.abspath(__file__)] + sys.argv[1:])
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

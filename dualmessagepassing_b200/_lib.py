@@ -19,6 +19,7 @@ SEG_NEGATE_OUT = 2
 ORDER_SCM = 0
 ORDER_UNC = 1
 ACT_NONE, ACT_RELU, ACT_LEAKY_RELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3, 4
+ACT_FROM_OUTPUT = 16
 
 _vp, _i64, _i32, _f32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_float
 
@@ -64,6 +65,30 @@ def check(rc, what):
     if rc != 0:
         msg = load().dmp_last_error().decode("utf-8", "replace")
         raise RuntimeError("%s failed (%d): %s" % (what, rc, msg))
+
+
+# ---- optional per-launch timing (bench.py): CUDA events on the launching stream around every C-ABI call
+PROFILE = None   # None = off; else list of (tag, start_event, end_event)
+LAUNCHES = 0     # number of C-ABI kernel-launching calls made so far (bench.py reports the delta)
+
+
+def call(name, device, *args, tag=None):
+    """Invoke one entry point on `device`'s current stream; raise on a non-zero status."""
+    global LAUNCHES
+    lib = load()
+    with torch.cuda.device(device):
+        if PROFILE is not None:
+            stream = torch.cuda.current_stream(device)
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            rc = getattr(lib, name)(*args)
+            e1.record(stream)
+            PROFILE.append((tag or name, e0, e1))
+        else:
+            rc = getattr(lib, name)(*args)
+    LAUNCHES += 1
+    check(rc, name)
 
 
 def ptr(t):

@@ -178,4 +178,16 @@ __device__ __forceinline__ float act_grad(float x, int act, float slope) {
   }
 }
 
+// derivative of the activation expressed through its OUTPUT y = act(x) (sign(y) == sign(x) for the
+// piecewise-linear ones as long as slope > 0)
+__device__ __forceinline__ float act_grad_from_output(float y, int act, float slope) {
+  switch (act) {
+    case DMP_ACT_RELU: return y > 0.f ? 1.f : 0.f;
+    case DMP_ACT_LEAKY_RELU: return y > 0.f ? 1.f : slope;
+    case DMP_ACT_TANH: return 1.f - y * y;
+    case DMP_ACT_SIGMOID: return y * (1.f - y);
+    default: return 1.f;
+  }
+}
+
 }  // namespace dmp

@@ -206,7 +206,10 @@ __global__ void __launch_bounds__(kThreads) gate_residual_kernel(const GateParam
         for (int k = 0; k < VEC; ++k) {
           float y = x.v[k];
           if (p.gate != nullptr) y = __fmul_rn(y, gate);
-          if (p.act != DMP_ACT_NONE) y = __fmul_rn(y, act_grad(pre.v[k], p.act, p.slope));
+          if (p.act != DMP_ACT_NONE)
+            y = __fmul_rn(y, (p.act & DMP_ACT_FROM_OUTPUT)
+                                 ? act_grad_from_output(pre.v[k], p.act & ~DMP_ACT_FROM_OUTPUT, p.slope)
+                                 : act_grad(pre.v[k], p.act, p.slope));
           o.v[k] = y;
         }
       }
@@ -324,7 +327,9 @@ static int gate_common(bool bwd, const float* x, int64_t ldx, const float* gate,
   DMP_CHECK_ARG(rows >= 0 && H >= 0, "gate_residual: negative size");
   if (rows == 0 || H == 0) return DMP_OK;
   DMP_CHECK_ARG(x && out && ldx >= H && ld_out >= H, "gate_residual: bad operands");
-  DMP_CHECK_ARG(act >= DMP_ACT_NONE && act <= DMP_ACT_SIGMOID, "gate_residual: bad activation %d", act);
+  DMP_CHECK_ARG((act & ~DMP_ACT_FROM_OUTPUT) >= DMP_ACT_NONE && (act & ~DMP_ACT_FROM_OUTPUT) <= DMP_ACT_SIGMOID &&
+                    (bwd || !(act & DMP_ACT_FROM_OUTPUT)),
+                "gate_residual: bad activation %d", act);
   DMP_CHECK_ARG(prev == nullptr || ld_prev >= H, "gate_residual: bad prev leading dimension");
   const int vec = pick_vec(H, {ldx, ld_out, prev ? ld_prev : 0}, {x, prev, out});
   const int64_t chunk = max_chunk(vec);
@@ -352,8 +357,10 @@ extern "C" int dmp_gate_residual_backward(const float* gout, int64_t ld_gout, co
                                           const float* gate, float* gx, int64_t ld_gx, int64_t rows,
                                           int64_t H, int act, float slope, void* stream) {
   using namespace dmp;
-  DMP_CHECK_ARG(act == DMP_ACT_NONE || x != nullptr, "gate_residual_backward: x required for act'");
+  DMP_CHECK_ARG((act & ~DMP_ACT_FROM_OUTPUT) == DMP_ACT_NONE || x != nullptr,
+                "gate_residual_backward: x required for act'");
   // kernel reads `x` slot = gout, `prev` slot = forward pre-activation
+  if ((act & ~DMP_ACT_FROM_OUTPUT) == DMP_ACT_NONE) act = DMP_ACT_NONE;
   return gate_common(true, gout, ld_gout, gate, act == DMP_ACT_NONE ? nullptr : x, ldx, gx, ld_gx, rows, H,
                      act, slope, stream);
 }

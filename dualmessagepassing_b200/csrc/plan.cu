@@ -41,10 +41,8 @@ __global__ void __launch_bounds__(kThreads) roles_kernel(
     a32[e] = a;
     b32[e] = b;
     atomicAdd(cnt_dst + d, 1);
-    if (cnt_a != nullptr) {
-      atomicAdd(cnt_a + a, 1);
-      atomicAdd(cnt_b + b, 1);
-    }
+    atomicAdd(cnt_a + a, 1);
+    atomicAdd(cnt_b + b, 1);
     if (cnt_src != nullptr) atomicAdd(cnt_src + s, 1ULL);
   }
 }
@@ -162,8 +160,7 @@ extern "C" int dmp_plan_build(const int64_t* src, const int64_t* dst, const uint
     const unsigned grid = (unsigned)(need < cap ? need : cap);
     static_assert(sizeof(unsigned long long) == sizeof(int64_t), "int64 atomics");
     roles_kernel<<<grid, kThreads, 0, stream>>>(
-        src, dst, rev, N, E, dst32, a32, b32, vals_in, cnt_dst, has_rev ? cnt_a : nullptr,
-        has_rev ? cnt_b : nullptr,
+        src, dst, rev, N, E, dst32, a32, b32, vals_in, cnt_dst, cnt_a, cnt_b,
         out_deg == nullptr ? reinterpret_cast<unsigned long long*>(out_deg_out) : nullptr, status);
     rc = launch_status("roles_kernel");
     if (rc != DMP_OK) return rc;
@@ -176,9 +173,9 @@ extern "C" int dmp_plan_build(const int64_t* src, const int64_t* dst, const uint
     DMP_CUDA_OK(cub::DeviceRadixSort::SortPairs(cub_ws, cub_bytes, (const int32_t*)dst32, keys_out,
                                                 (const uint32_t*)vals_in, reinterpret_cast<uint32_t*>(csc_eid),
                                                 (int)E, 0, bits, stream));
+  DMP_CUDA_OK(cub::DeviceScan::ExclusiveSum(cub_ws, cub_bytes, cnt_a, a_indptr, (int)(N + 1), stream));
+  DMP_CUDA_OK(cub::DeviceScan::ExclusiveSum(cub_ws, cub_bytes, cnt_b, b_indptr, (int)(N + 1), stream));
   if (has_rev) {
-    DMP_CUDA_OK(cub::DeviceScan::ExclusiveSum(cub_ws, cub_bytes, cnt_a, a_indptr, (int)(N + 1), stream));
-    DMP_CUDA_OK(cub::DeviceScan::ExclusiveSum(cub_ws, cub_bytes, cnt_b, b_indptr, (int)(N + 1), stream));
     if (E > 0) {
       DMP_CUDA_OK(cub::DeviceRadixSort::SortPairs(cub_ws, cub_bytes, (const int32_t*)a32, keys_out,
                                                   (const uint32_t*)vals_in, reinterpret_cast<uint32_t*>(a_eid),
@@ -188,12 +185,9 @@ extern "C" int dmp_plan_build(const int64_t* src, const int64_t* dst, const uint
                                                   (int)E, 0, bits, stream));
     }
   } else {
-    // a == dst: the a-structure is the CSC; b == src: CSR.  Histogram of src == out-degree unless the
-    // caller supplied out_deg, so count it separately through cnt_b.
-    DMP_CUDA_OK(cudaMemcpyAsync(a_indptr, csc_indptr, (N + 1) * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
+    // a == dst: the a-structure is the CSC (copied, not re-sorted); b == src: the CSR.
     if (E > 0) {
       DMP_CUDA_OK(cudaMemcpyAsync(a_eid, csc_eid, E * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
-      // second roles pass is avoided: sort by b32 (= src) and derive indptr from a histogram of b32
       DMP_CUDA_OK(cub::DeviceRadixSort::SortPairs(cub_ws, cub_bytes, (const int32_t*)b32, keys_out,
                                                   (const uint32_t*)vals_in, reinterpret_cast<uint32_t*>(b_eid),
                                                   (int)E, 0, bits, stream));

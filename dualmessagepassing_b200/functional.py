@@ -18,7 +18,8 @@ def _stream(t):
     return _lib.stream_ptr(t.device)
 
 
-def segment_reduce(indptr, eid, V, H, *, w_perm=None, rev_col_offset=0, base=None, bias=None, mode=0, out=None):
+def segment_reduce(indptr, eid, V, H, *, w_perm=None, rev_col_offset=0, base=None, bias=None, mode=0, out=None,
+                   tag=None):
     """Raw (non-differentiable) call of dmp_segment_reduce. V: [*, ldV] fp32, returns [nseg, H]."""
     _lib.require_cuda(indptr, eid, V, w_perm, base, bias)
     V, ldV = _lib.row_major(V)
@@ -32,11 +33,10 @@ def segment_reduce(indptr, eid, V, H, *, w_perm=None, rev_col_offset=0, base=Non
         bias = bias.contiguous()
     out_m, ld_out = _lib.row_major(out)
     assert out_m.data_ptr() == out.data_ptr(), "out must have dense rows"
-    with torch.cuda.device(V.device):
-        _lib.check(_lib.load().dmp_segment_reduce(
-            _lib.ptr(indptr), _lib.ptr(eid), _lib.ptr(w_perm), _lib.ptr(V), ldV, rev_col_offset,
-            _lib.ptr(base), ld_base, _lib.ptr(bias), _lib.ptr(out), ld_out, nseg, H, mode, _stream(V)),
-            "dmp_segment_reduce")
+    _lib.call("dmp_segment_reduce", V.device,
+              _lib.ptr(indptr), _lib.ptr(eid), _lib.ptr(w_perm), _lib.ptr(V), ldV, rev_col_offset,
+              _lib.ptr(base), ld_base, _lib.ptr(bias), _lib.ptr(out), ld_out, nseg, H, mode, _stream(V),
+              tag=tag or "segment_reduce")
     return out
 
 
@@ -56,11 +56,10 @@ def edge_update(plan, S, P, Qd, Qs, ebias, order, out=None, edge_agg=None):
         _, ld_agg = _lib.row_major(edge_agg)
     if ebias is not None:
         ebias = ebias.contiguous()
-    with torch.cuda.device(S.device):
-        _lib.check(_lib.load().dmp_edge_update(
-            _lib.ptr(plan.a32), _lib.ptr(plan.b32), _lib.ptr(plan.coef), _lib.ptr(S), ldS, _lib.ptr(P), ldP,
-            _lib.ptr(Qd), ldQd, _lib.ptr(Qs), ldQs, _lib.ptr(ebias), _lib.ptr(out), ld_out,
-            _lib.ptr(edge_agg), ld_agg, E, H, order, _stream(S)), "dmp_edge_update")
+    _lib.call("dmp_edge_update", S.device,
+              _lib.ptr(plan.a32), _lib.ptr(plan.b32), _lib.ptr(plan.coef), _lib.ptr(S), ldS, _lib.ptr(P), ldP,
+              _lib.ptr(Qd), ldQd, _lib.ptr(Qs), ldQs, _lib.ptr(ebias), _lib.ptr(out), ld_out,
+              _lib.ptr(edge_agg), ld_agg, E, H, order, _stream(S), tag="edge_update")
     return out
 
 
@@ -82,12 +81,11 @@ def edge_backward(plan, norm_flat, gN, gE, *, want_T=True, want_CG=True, t_rev_c
         if CG is None:
             CG = torch.empty((plan.E, H), dtype=torch.float32, device=dev)
         _, ldCG = _lib.row_major(CG)
-    with torch.cuda.device(dev):
-        _lib.check(_lib.load().dmp_edge_backward(
-            _lib.ptr(plan.dst32), _lib.ptr(plan.rev), _lib.ptr(norm_flat), _lib.ptr(plan.coef),
-            _lib.ptr(gN if want_T else None), ld_gN, _lib.ptr(gE if want_CG else None), ld_gE,
-            _lib.ptr(T if want_T else None), ldT, t_rev_col_offset, _lib.ptr(CG if want_CG else None), ldCG,
-            plan.E, H, _lib.stream_ptr(dev)), "dmp_edge_backward")
+    _lib.call("dmp_edge_backward", dev,
+              _lib.ptr(plan.dst32), _lib.ptr(plan.rev), _lib.ptr(norm_flat), _lib.ptr(plan.coef),
+              _lib.ptr(gN if want_T else None), ld_gN, _lib.ptr(gE if want_CG else None), ld_gE,
+              _lib.ptr(T if want_T else None), ldT, t_rev_col_offset, _lib.ptr(CG if want_CG else None), ldCG,
+              plan.E, H, _lib.stream_ptr(dev), tag="edge_backward")
     return (T if want_T else None), (CG if want_CG else None)
 
 
@@ -101,7 +99,8 @@ class _SparseCore(torch.autograd.Function):
         if norm is not None:
             norm_flat, norm_perm = plan.norm_permuted(norm)
         node_pre = segment_reduce(plan.csc_indptr, plan.csc_eid, M, H, w_perm=norm_perm,
-                                  rev_col_offset=m_rev_off, base=Ln, bias=nbias, mode=_lib.SEG_SIGN_BY_REV)
+                                  rev_col_offset=m_rev_off, base=Ln, bias=nbias, mode=_lib.SEG_SIGN_BY_REV,
+                                  tag="segment_reduce.node_fwd")
         edge_pre = edge_update(plan, S, P, Qd, Qs, ebias, order)
         ctx.plan, ctx.norm_flat, ctx.m_rev_off, ctx.H = plan, norm_flat, m_rev_off, H
         ctx.m_cols = M.shape[1]
@@ -122,9 +121,10 @@ class _SparseCore(torch.autograd.Function):
             dM, dP = edge_backward(plan, ctx.norm_flat, gN, gE, want_T=need[4], want_CG=need[6],
                                    t_rev_col_offset=ctx.m_rev_off, T=T)
         if need[8]:
-            dQd = segment_reduce(plan.a_indptr, plan.a_eid, gE, H)
+            dQd = segment_reduce(plan.a_indptr, plan.a_eid, gE, H, tag="segment_reduce.dQd_bwd")
         if need[9]:
-            dQs = segment_reduce(plan.b_indptr, plan.b_eid, gE, H, mode=_lib.SEG_NEGATE_OUT)
+            dQs = segment_reduce(plan.b_indptr, plan.b_eid, gE, H, mode=_lib.SEG_NEGATE_OUT,
+                                 tag="segment_reduce.dQs_bwd")
         if ctx.has_bias[0] and need[10]:
             dnb = gN.sum(0)
         if ctx.has_bias[1] and need[11]:
@@ -158,10 +158,8 @@ class _GateResidual(torch.autograd.Function):
         g = None
         if gate is not None:
             g = gate.reshape(-1).contiguous().float()
-        with torch.cuda.device(x.device):
-            _lib.check(_lib.load().dmp_gate_residual(_lib.ptr(x), ldx, _lib.ptr(g), _lib.ptr(prev), ld_prev,
-                                                     _lib.ptr(out), H, rows, H, act, slope, _stream(x)),
-                       "dmp_gate_residual")
+        _lib.call("dmp_gate_residual", x.device, _lib.ptr(x), ldx, _lib.ptr(g), _lib.ptr(prev), ld_prev,
+                  _lib.ptr(out), H, rows, H, act, slope, _stream(x), tag="gate_residual")
         ctx.save_for_backward(x if act != _lib.ACT_NONE else None, g)
         ctx.act, ctx.slope, ctx.has_prev = act, slope, prev is not None
         return out
@@ -177,14 +175,15 @@ class _GateResidual(torch.autograd.Function):
                 gx = gout
             else:
                 gx = torch.empty_like(gout)
-                with torch.cuda.device(gout.device):
-                    _lib.check(_lib.load().dmp_gate_residual_backward(
-                        _lib.ptr(gout), ldg, _lib.ptr(x), H, _lib.ptr(g), _lib.ptr(gx), H, rows, H, ctx.act,
-                        ctx.slope, _stream(gout)), "dmp_gate_residual_backward")
+                _lib.call("dmp_gate_residual_backward", gout.device,
+                          _lib.ptr(gout), ldg, _lib.ptr(x), H, _lib.ptr(g), _lib.ptr(gx), H, rows, H, ctx.act,
+                          ctx.slope, _stream(gout), tag="gate_residual_bwd")
         gprev = gout if (ctx.has_prev and ctx.needs_input_grad[2]) else None
         return gx, None, gprev, None, None
 
 
 def gate_residual(x, gate=None, prev=None, act="none", slope=0.0):
     """Fused `prev + gate * act(x)`; gate is [rows] or [rows,1] (0/1 mask or soft gate), no grad to it."""
+    if gate is not None and gate.requires_grad:
+        raise NotImplementedError("gate_residual does not differentiate with respect to the gate")
     return _GateResidual.apply(x, gate, prev, _ACT_IDS[act], float(slope))

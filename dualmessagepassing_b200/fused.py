@@ -1,0 +1,222 @@
+"""Whole-layer autograd function with explicit buffer management (the path used at BASELINE scale).
+
+`torch.autograd` over the composed ops of `layers.dual_message_passing` keeps ~14 edge-sized
+temporaries alive (the reference keeps even more); at config 5
+(E = 40 M, H = 128) one [E,H] fp32 tensor is 20.5 GB, so that composition does not fit 180 GB of HBM.
+This function computes exactly the same quantities in the same order but owns every edge-sized
+buffer: forward keeps only {X_e (input), edge_pre, h1}; backward re-uses the saved buffers in place.
+Peak is 5 edge-sized tensors in forward and 7 in backward including the caller's input, output and
+upstream gradient ("Memory plan").
+
+Supported: SCM flavour or UNC flavour without BatchNorm, num_mlp_layers in {0, 2}, activation in
+{none, relu, leaky_relu, tanh, sigmoid}, dropout inactive.  Anything else runs the composed path.
+Reference lines: SubgraphCountingMatching/models/dmpnn.py:111-156 (forward), SURVEY.md Appendix A.2
+(backward).
+"""
+import torch
+
+from . import _lib
+from .functional import edge_backward, edge_update, segment_reduce
+
+_ACT = {"none": _lib.ACT_NONE, "relu": _lib.ACT_RELU, "leaky_relu": _lib.ACT_LEAKY_RELU,
+        "tanh": _lib.ACT_TANH, "sigmoid": _lib.ACT_SIGMOID}
+
+
+def supported_activation(name):
+    return name in _ACT
+
+
+def _act_inplace(x, act, slope):
+    """x <- act(x) with the sm_100a elementwise kernel (in place)."""
+    if act == _lib.ACT_NONE or x.numel() == 0:
+        return x
+    rows, H = x.shape
+    _lib.call("dmp_gate_residual", x.device, _lib.ptr(x), H, None, None, 0, _lib.ptr(x), H, rows, H, act,
+              slope, _lib.stream_ptr(x.device), tag="act_inplace")
+    return x
+
+
+def _act_backward_inplace(g, y, act, slope):
+    """g <- g * act'(.) expressed through the activation OUTPUT y (in place on g)."""
+    if act == _lib.ACT_NONE or g.numel() == 0:
+        return g
+    rows, H = g.shape
+    _lib.call("dmp_gate_residual_backward", g.device,
+              _lib.ptr(g), H, _lib.ptr(y), H, None, _lib.ptr(g), H, rows, H, act | _lib.ACT_FROM_OUTPUT, slope,
+              _lib.stream_ptr(g.device), tag="act_bwd_inplace")
+    return g
+
+
+def _mlp_forward(pre, W1, b1, W2, b2, act, slope):
+    """Linear -> act -> Linear (dmpnn.py:45-52 without BN). Returns (out, h1) with h1 = act(lin1)."""
+    h1 = torch.addmm(b1, pre, W1.t()) if b1 is not None else pre @ W1.t()
+    _act_inplace(h1, act, slope)
+    out = torch.addmm(b2, h1, W2.t()) if b2 is not None else h1 @ W2.t()
+    return out, h1
+
+
+def _mlp_backward(g_out, pre, h1, W1, W2, act, slope, need_w):
+    """Returns (g_pre written into h1's storage, dW1, db1, dW2, db2). Consumes h1."""
+    dW2 = db2 = dW1 = db1 = None
+    if need_w:
+        dW2 = g_out.t() @ h1
+        db2 = g_out.sum(0)
+    g1 = g_out @ W2                      # new edge-sized buffer
+    _act_backward_inplace(g1, h1, act, slope)
+    if need_w:
+        dW1 = g1.t() @ pre
+        db1 = g1.sum(0)
+    g_pre = torch.mm(g1, W1, out=h1)     # h1 is dead: re-use its storage
+    return g_pre, g1, dW1, db1, dW2, db2
+
+
+class _FusedDMPLayer(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan, cfg, X_v, X_e, norm, in_w, out_w, src_w, dst_w, nloop_w, eloop_w, nbias, ebias,
+                nW1, nb1, nW2, nb2, eW1, eb1, eW2, eb2):
+        order, act, slope, has_mlp = cfg
+        H = nloop_w.shape[1]
+        E, N = plan.E, plan.N
+        norm_flat = norm_perm = None
+        if norm is not None:
+            norm_flat, norm_perm = plan.norm_permuted(norm)
+
+        # ---- node side (dmpnn.py:113-133): project, aggregate incident edge messages, self loop, bias
+        Ln = X_v @ nloop_w
+        if plan.rev_layout == "none":
+            M, m_off = X_e @ in_w, 0
+        elif plan.rev_layout == "halves":
+            h = E // 2
+            M, m_off = torch.empty((E, H), dtype=X_e.dtype, device=X_e.device), 0
+            torch.mm(X_e[:h], in_w, out=M[:h])
+            torch.mm(X_e[h:], out_w, out=M[h:])
+        else:
+            M, m_off = X_e @ torch.cat([in_w, out_w], dim=1), H
+        node_pre = segment_reduce(plan.csc_indptr, plan.csc_eid, M, H, w_perm=norm_perm, rev_col_offset=m_off,
+                                  base=Ln, bias=nbias, mode=_lib.SEG_SIGN_BY_REV, out=Ln,
+                                  tag="segment_reduce.node_fwd")
+        del M
+
+        # ---- edge side (dmpnn.py:112-123,142-149): endpoint gather, degree term, self loop, bias
+        Qd = X_v @ dst_w
+        Qs = X_v @ src_w
+        P = X_e @ (src_w - dst_w)
+        S = X_e @ eloop_w
+        edge_pre = edge_update(plan, S, P, Qd, Qs, ebias, order, out=S)
+        del P, Qd, Qs
+
+        if has_mlp:
+            node_out, nh1 = _mlp_forward(node_pre, nW1, nb1, nW2, nb2, act, slope)
+            edge_out, eh1 = _mlp_forward(edge_pre, eW1, eb1, eW2, eb2, act, slope)
+        else:
+            # act(pre) in place: backward only needs the output (act' from output)
+            node_out, nh1 = _act_inplace(node_pre, act, slope), None
+            edge_out, eh1 = _act_inplace(edge_pre, act, slope), None
+            node_pre = edge_pre = None
+        ctx.plan, ctx.cfg, ctx.norm_flat, ctx.m_off = plan, cfg, norm_flat, m_off
+        ctx.save_for_backward(X_v, X_e, in_w, out_w, src_w, dst_w, nloop_w, eloop_w, nW1, nW2, eW1, eW2,
+                              node_pre, nh1, edge_pre, eh1,
+                              node_out if not has_mlp else None, edge_out if not has_mlp else None)
+        ctx.has_bias = (nbias is not None, ebias is not None)
+        ctx.mlp_bias = (nb1 is not None, nb2 is not None, eb1 is not None, eb2 is not None)
+        return node_out, edge_out
+
+    @staticmethod
+    def backward(ctx, g_node_out, g_edge_out):
+        (X_v, X_e, in_w, out_w, src_w, dst_w, nloop_w, eloop_w, nW1, nW2, eW1, eW2,
+         node_pre, nh1, edge_pre, eh1, node_act, edge_act) = ctx.saved_tensors
+        plan = ctx.plan
+        if getattr(ctx, "consumed", False):
+            raise RuntimeError("the fused DMPNN layer re-uses its saved buffers in backward and cannot be "
+                               "back-propagated twice (retain_graph); set layer.fused = False for that")
+        ctx.consumed = True
+        order, act, slope, has_mlp = ctx.cfg
+        H = nloop_w.shape[1]
+        E = plan.E
+        need = ctx.needs_input_grad
+        need_xv, need_xe = need[2], need[3]
+        need_w = any(need[5:])
+        g_node_out = g_node_out.contiguous()
+        g_edge_out = g_edge_out.contiguous()
+        dnW1 = dnb1 = dnW2 = dnb2 = deW1 = deb1 = deW2 = deb2 = None
+
+        # ---- through the MLP / activation: gN = dL/dnode_pre, gE = dL/dedge_pre -------------------------
+        if has_mlp:
+            gN, _, dnW1, dnb1, dnW2, dnb2 = _mlp_backward(g_node_out, node_pre, nh1, nW1, nW2, act, slope, need_w)
+            gE, buf, deW1, deb1, deW2, deb2 = _mlp_backward(g_edge_out, edge_pre, eh1, eW1, eW2, act, slope, need_w)
+            buf2 = edge_pre  # dead after dW1: second scratch buffer
+        else:
+            gN = _act_backward_inplace(g_node_out.clone(), node_act, act, slope)
+            gE = _act_backward_inplace(g_edge_out.clone(), edge_act, act, slope)
+            buf = buf2 = None
+        del node_pre, nh1, edge_pre, eh1
+
+        # ---- sparse core backward: two sorted-segment sums of gE, one gather of gN ------
+        dQd = segment_reduce(plan.a_indptr, plan.a_eid, gE, H, tag="segment_reduce.dQd_bwd")
+        dQs = segment_reduce(plan.b_indptr, plan.b_eid, gE, H, mode=_lib.SEG_NEGATE_OUT,
+                             tag="segment_reduce.dQs_bwd")
+        m_cols = H + ctx.m_off
+        if buf is not None and ctx.m_off == 0:
+            T = buf
+        else:
+            T = torch.zeros((E, m_cols), dtype=gE.dtype, device=gE.device) if ctx.m_off else \
+                torch.empty((E, H), dtype=gE.dtype, device=gE.device)
+        CG = buf2 if buf2 is not None else torch.empty((E, H), dtype=gE.dtype, device=gE.device)
+        edge_backward(plan, ctx.norm_flat, gN, gE, t_rev_col_offset=ctx.m_off, T=T, CG=CG)
+
+        # ---- dense backward --------------------------------------------------------------------------------
+        w_sd = src_w - dst_w
+        dX_v = dX_e = None
+        if need_xv:
+            dX_v = gN @ nloop_w.t()
+            dX_v.addmm_(dQd, dst_w.t())
+            dX_v.addmm_(dQs, src_w.t())
+        if need_xe:
+            dX_e = gE @ eloop_w.t()
+            dX_e.addmm_(CG, w_sd.t())
+            if plan.rev_layout == "none":
+                dX_e.addmm_(T, in_w.t())
+            elif plan.rev_layout == "halves":
+                h = E // 2
+                dX_e[:h].addmm_(T[:h], in_w.t())
+                dX_e[h:].addmm_(T[h:], out_w.t())
+            else:
+                dX_e.addmm_(T, torch.cat([in_w, out_w], dim=1).t())
+        d_in = d_out = d_src = d_dst = d_nloop = d_eloop = d_nb = d_eb = None
+        if need_w:
+            d_nloop = X_v.t() @ gN
+            d_eloop = X_e.t() @ gE
+            d_sd = X_e.t() @ CG
+            d_dst = X_v.t() @ dQd
+            d_dst.sub_(d_sd)
+            d_src = X_v.t() @ dQs
+            d_src.add_(d_sd)
+            if plan.rev_layout == "none":
+                d_in = X_e.t() @ T
+                d_out = torch.zeros_like(out_w)
+            elif plan.rev_layout == "halves":
+                h = E // 2
+                d_in = X_e[:h].t() @ T[:h]
+                d_out = X_e[h:].t() @ T[h:]
+            else:
+                d_io = X_e.t() @ T
+                d_in, d_out = d_io[:, :H].contiguous(), d_io[:, H:].contiguous()
+            if ctx.has_bias[0]:
+                d_nb = gN.sum(0)
+            if ctx.has_bias[1]:
+                d_eb = gE.sum(0)
+        mb = ctx.mlp_bias
+        return (None, None, dX_v, dX_e, None, d_in, d_out, d_src, d_dst, d_nloop, d_eloop, d_nb, d_eb,
+                dnW1, dnb1 if mb[0] else None, dnW2, dnb2 if mb[1] else None,
+                deW1, deb1 if mb[2] else None, deW2, deb2 if mb[3] else None)
+
+
+def fused_dmp_layer(plan, X_v, X_e, weights, nbias, ebias, nmlp, emlp, *, act_func, slope, order, norm=None):
+    """weights = (in, out, src, dst, nloop, eloop); nmlp/emlp = (W1, b1, W2, b2) or None."""
+    _lib.require_cuda(X_v, X_e)
+    has_mlp = nmlp is not None
+    cfg = (order, _ACT[act_func], float(slope), has_mlp)
+    n = nmlp if has_mlp else (None,) * 4
+    e = emlp if has_mlp else (None,) * 4
+    return _FusedDMPLayer.apply(plan, cfg, X_v.contiguous(), X_e.contiguous(), norm, *weights, nbias, ebias,
+                                *n, *e)

@@ -21,6 +21,7 @@ from .act import map_activation_str_to_layer
 from .constants import (EDGEFEAT, LEAKY_RELU_A, NODEFEAT, OUTDEGREE, REVFLAG, UNC_FEAT, UNC_NORM,
                         UNC_OUTDEGREE, UNC_REVFLAG)
 from .functional import sparse_core
+from .fused import fused_dmp_layer, supported_activation
 from .init import init_module, init_weight
 from .plan import get_plan
 
@@ -92,6 +93,11 @@ class DMPLayer(nn.Module):
         self.input_dim = input_dim
         self.hidden_dim = hidden_dim
         self.act_func = act_func
+        self.num_mlp_layers = num_mlp_layers
+        self.batch_norm = batch_norm
+        # "auto": whole-layer function with explicit buffer re-use (fused.py) whenever the configuration
+        # allows it; False forces the composed autograd path (same kernels, torch-managed memory)
+        self.fused = "auto"
 
         def weight():
             return nn.Parameter(torch.empty(input_dim, hidden_dim))
@@ -143,11 +149,27 @@ class DMPLayer(nn.Module):
             self.dst_weight.div_(init_eeigenv)
             self.eloop_weight.div_(init_eeigenv)
 
+    def _use_fused(self):
+        if not self.fused:
+            return False
+        mlp_ok = self.num_mlp_layers == 0 or (self.num_mlp_layers == 2 and not self.batch_norm)
+        drop_ok = (not self.training) or self.drop.p == 0
+        return mlp_ok and drop_ok and supported_activation(self.act_func)
+
     def forward(self, graph, node_feat, edge_feat):
         plan = get_plan(graph, REVFLAG, OUTDEGREE)
         # frame side effects of dmpnn.py:96-109 (inputs stay bound to the graph)
         graph.ndata[NODEFEAT] = node_feat
         graph.edata[EDGEFEAT] = edge_feat
+        if self._use_fused():
+            weights = (self.in_weight, self.out_weight, self.src_weight, self.dst_weight, self.nloop_weight,
+                       self.eloop_weight)
+            nmlp = emlp = None
+            if self.num_mlp_layers == 2:
+                nmlp = (self.nmlp[0].weight, self.nmlp[0].bias, self.nmlp[2].weight, self.nmlp[2].bias)
+                emlp = (self.emlp[0].weight, self.emlp[0].bias, self.emlp[2].weight, self.emlp[2].bias)
+            return fused_dmp_layer(plan, node_feat.float(), edge_feat.float(), weights, self.nbias, self.ebias,
+                                   nmlp, emlp, act_func=self.act_func, slope=LEAKY_RELU_A, order=_lib.ORDER_SCM)
         node_pre, edge_pre = dual_message_passing(
             plan, node_feat, edge_feat, self.in_weight, self.out_weight, self.src_weight, self.dst_weight,
             self.nloop_weight, self.eloop_weight, self.nbias, self.ebias, order=_lib.ORDER_SCM)

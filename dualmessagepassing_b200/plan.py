@@ -108,10 +108,8 @@ class DMPPlan:
             if flat.numel() != self.E:
                 raise ValueError("edge_norm must have one entry per edge")
             out = torch.empty_like(flat)
-            with torch.cuda.device(self.device):
-                _lib.check(_lib.load().dmp_permute_edge_scalar(_lib.ptr(self.csc_eid), _lib.ptr(flat), _lib.ptr(out),
-                                                               self.E, _lib.stream_ptr(self.device)),
-                           "dmp_permute_edge_scalar")
+            _lib.call("dmp_permute_edge_scalar", self.device, _lib.ptr(self.csc_eid), _lib.ptr(flat),
+                      _lib.ptr(out), self.E, _lib.stream_ptr(self.device))
             self._norm_perm = {key: (flat, out)}
             hit = self._norm_perm[key]
         return hit

@@ -58,6 +58,9 @@ extern "C" {
 #define DMP_ACT_LEAKY_RELU 2 /* slope passed explicitly (reference: 1/5.5, constants.py:10) */
 #define DMP_ACT_TANH 3
 #define DMP_ACT_SIGMOID 4
+/* dmp_gate_residual_backward only: OR-ed into `act` when `x` holds the activation OUTPUT y = act(pre)
+ * instead of the pre-activation (lets the forward apply the activation in place and keep one tensor) */
+#define DMP_ACT_FROM_OUTPUT 16
 
 DMP_API const char* dmp_last_error(void);
 DMP_API int dmp_version(void);

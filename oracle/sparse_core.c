@@ -120,6 +120,16 @@ static float act_g(float x, int act, float slope) {
   }
 }
 
+static float act_g_out(float y, int act, float slope) {
+  switch (act) {
+    case 1: return y > 0.f ? 1.f : 0.f;
+    case 2: return y > 0.f ? 1.f : slope;
+    case 3: return 1.f - y * y;
+    case 4: return y * (1.f - y);
+    default: return 1.f;
+  }
+}
+
 /* dmpnn.py:236-241,266-275: out = prev + gate * act(x) */
 void oracle_gate_residual(const float* x, int64_t ldx, const float* gate, const float* prev, int64_t ld_prev,
                           float* out, int64_t ld_out, int64_t rows, int64_t H, int act, float slope) {
@@ -139,7 +149,8 @@ void oracle_gate_residual_backward(const float* gout, int64_t ld_gout, const flo
     for (int64_t h = 0; h < H; ++h) {
       float y = gout[r * ld_gout + h];
       if (gate) y = y * gate[r];
-      if (act != 0) y = y * act_g(x[r * ldx + h], act, slope);
+      if ((act & ~16) != 0)
+        y = y * ((act & 16) ? act_g_out(x[r * ldx + h], act & ~16, slope) : act_g(x[r * ldx + h], act, slope));
       gx[r * ld_gx + h] = y;
     }
 }
