@@ -73,13 +73,20 @@ def _mlp_backward(g_out, pre, h1, W1, W2, act, slope, need_w):
 class _FusedDMPLayer(torch.autograd.Function):
     @staticmethod
     def forward(ctx, plan, cfg, X_v, X_e, norm, in_w, out_w, src_w, dst_w, nloop_w, eloop_w, nbias, ebias,
-                nW1, nb1, nW2, nb2, eW1, eb1, eW2, eb2):
+                nW1, nb1, nW2, nb2, eW1, eb1, eW2, eb2, part=None):
         order, act, slope, has_mlp = cfg
         H = nloop_w.shape[1]
         E, N = plan.E, plan.N
         norm_flat = norm_perm = None
         if norm is not None:
             norm_flat, norm_perm = plan.norm_permuted(norm)
+        # destination-range partition (parallel.py): X_v holds only the owned node rows; gather the rest
+        csc_indptr, X_v_full = plan.csc_indptr, X_v
+        if part is not None:
+            from .parallel import all_gather_rows
+            n_lo, n_hi, group = part
+            X_v_full = all_gather_rows(X_v, group)
+            csc_indptr = plan.csc_indptr[n_lo:n_hi + 1]
 
         # ---- node side (dmpnn.py:113-133): project, aggregate incident edge messages, self loop, bias
         Ln = X_v @ nloop_w
@@ -92,14 +99,14 @@ class _FusedDMPLayer(torch.autograd.Function):
             torch.mm(X_e[h:], out_w, out=M[h:])
         else:
             M, m_off = X_e @ torch.cat([in_w, out_w], dim=1), H
-        node_pre = segment_reduce(plan.csc_indptr, plan.csc_eid, M, H, w_perm=norm_perm, rev_col_offset=m_off,
+        node_pre = segment_reduce(csc_indptr, plan.csc_eid, M, H, w_perm=norm_perm, rev_col_offset=m_off,
                                   base=Ln, bias=nbias, mode=_lib.SEG_SIGN_BY_REV, out=Ln,
                                   tag="segment_reduce.node_fwd")
         del M
 
         # ---- edge side (dmpnn.py:112-123,142-149): endpoint gather, degree term, self loop, bias
-        Qd = X_v @ dst_w
-        Qs = X_v @ src_w
+        Qd = X_v_full @ dst_w
+        Qs = X_v_full @ src_w
         P = X_e @ (src_w - dst_w)
         S = X_e @ eloop_w
         edge_pre = edge_update(plan, S, P, Qd, Qs, ebias, order, out=S)
@@ -113,7 +120,8 @@ class _FusedDMPLayer(torch.autograd.Function):
             node_out, nh1 = _act_inplace(node_pre, act, slope), None
             edge_out, eh1 = _act_inplace(edge_pre, act, slope), None
             node_pre = edge_pre = None
-        ctx.plan, ctx.cfg, ctx.norm_flat, ctx.m_off = plan, cfg, norm_flat, m_off
+        ctx.plan, ctx.cfg, ctx.norm_flat, ctx.m_off, ctx.part = plan, cfg, norm_flat, m_off, part
+        ctx.X_v_full = X_v_full if part is not None else None
         ctx.save_for_backward(X_v, X_e, in_w, out_w, src_w, dst_w, nloop_w, eloop_w, nW1, nW2, eW1, eW2,
                               node_pre, nh1, edge_pre, eh1,
                               node_out if not has_mlp else None, edge_out if not has_mlp else None)
@@ -150,6 +158,14 @@ class _FusedDMPLayer(torch.autograd.Function):
             gE = _act_backward_inplace(g_edge_out.clone(), edge_act, act, slope)
             buf = buf2 = None
         del node_pre, nh1, edge_pre, eh1
+        part = ctx.part
+        X_v_full, gN_full = X_v, gN
+        if part is not None:
+            from .parallel import allreduce_tensors_, reduce_scatter_rows
+            n_lo, n_hi, group = part
+            X_v_full = ctx.X_v_full
+            gN_full = torch.zeros((plan.N, H), dtype=gN.dtype, device=gN.device)
+            gN_full[n_lo:n_hi] = gN  # edge_backward indexes gN by GLOBAL destination id
 
         # ---- sparse core backward: two sorted-segment sums of gE, one gather of gN ------
         dQd = segment_reduce(plan.a_indptr, plan.a_eid, gE, H, tag="segment_reduce.dQd_bwd")
@@ -162,15 +178,24 @@ class _FusedDMPLayer(torch.autograd.Function):
             T = torch.zeros((E, m_cols), dtype=gE.dtype, device=gE.device) if ctx.m_off else \
                 torch.empty((E, H), dtype=gE.dtype, device=gE.device)
         CG = buf2 if buf2 is not None else torch.empty((E, H), dtype=gE.dtype, device=gE.device)
-        edge_backward(plan, ctx.norm_flat, gN, gE, t_rev_col_offset=ctx.m_off, T=T, CG=CG)
+        edge_backward(plan, ctx.norm_flat, gN_full, gE, t_rev_col_offset=ctx.m_off, T=T, CG=CG)
+        del gN_full
 
         # ---- dense backward --------------------------------------------------------------------------------
         w_sd = src_w - dst_w
         dX_v = dX_e = None
         if need_xv:
-            dX_v = gN @ nloop_w.t()
-            dX_v.addmm_(dQd, dst_w.t())
-            dX_v.addmm_(dQs, src_w.t())
+            if part is None:
+                dX_v = gN @ nloop_w.t()
+                dX_v.addmm_(dQd, dst_w.t())
+                dX_v.addmm_(dQs, src_w.t())
+            else:
+                # partial sums over this rank's edges for EVERY node -> owners (reduce-scatter over NVLink)
+                partial = dQd @ dst_w.t()
+                partial.addmm_(dQs, src_w.t())
+                dX_v = reduce_scatter_rows(partial, group)
+                dX_v.addmm_(gN, nloop_w.t())
+                del partial
         if need_xe:
             dX_e = gE @ eloop_w.t()
             dX_e.addmm_(CG, w_sd.t())
@@ -187,9 +212,9 @@ class _FusedDMPLayer(torch.autograd.Function):
             d_nloop = X_v.t() @ gN
             d_eloop = X_e.t() @ gE
             d_sd = X_e.t() @ CG
-            d_dst = X_v.t() @ dQd
+            d_dst = X_v_full.t() @ dQd
             d_dst.sub_(d_sd)
-            d_src = X_v.t() @ dQs
+            d_src = X_v_full.t() @ dQs
             d_src.add_(d_sd)
             if plan.rev_layout == "none":
                 d_in = X_e.t() @ T
@@ -206,9 +231,13 @@ class _FusedDMPLayer(torch.autograd.Function):
             if ctx.has_bias[1]:
                 d_eb = gE.sum(0)
         mb = ctx.mlp_bias
+        if part is not None and need_w:
+            # every weight gradient above is a partial sum over this rank's nodes/edges
+            allreduce_tensors_([d_in, d_out, d_src, d_dst, d_nloop, d_eloop, d_nb, d_eb, dnW1, dnb1, dnW2, dnb2,
+                                deW1, deb1, deW2, deb2], group)
         return (None, None, dX_v, dX_e, None, d_in, d_out, d_src, d_dst, d_nloop, d_eloop, d_nb, d_eb,
                 dnW1, dnb1 if mb[0] else None, dnW2, dnb2 if mb[1] else None,
-                deW1, deb1 if mb[2] else None, deW2, deb2 if mb[3] else None)
+                deW1, deb1 if mb[2] else None, deW2, deb2 if mb[3] else None, None)
 
 
 def fused_dmp_layer(plan, X_v, X_e, weights, nbias, ebias, nmlp, emlp, *, act_func, slope, order, norm=None):

@@ -58,7 +58,10 @@ def test_dmplayer_matches_reference_golden(name):
     close(xe.grad, case["grad_edge_feat"], "grad_edge_feat")
     for k, p in layer.named_parameters():
         got = p.grad if p.grad is not None else torch.zeros_like(p)
-        close(got, case["grads"][k], "grad " + k)
+        # parameter gradients are fp32 sums over all nodes / edges (with exact cancellation to 0 for a bias
+        # in front of BatchNorm): absolute noise floor ~ sqrt(rows) * eps * |term| ~ 1e-5, for the reference too
+        torch.testing.assert_close(got.cpu(), case["grads"][k], rtol=1e-5,
+                                   atol=2e-5 * max(1.0, float(case["grads"][k].abs().max())), msg=lambda m: k + m)
 
 
 @pytest.mark.parametrize("name", _golden.case_names("unc_"))
