@@ -145,4 +145,6 @@ def test_partitioned_algorithm_equals_single_graph_oracle():
         torch.testing.assert_close(gxe, xe.grad[ids], rtol=1e-5, atol=1e-6)
         torch.testing.assert_close(gxv, xv.grad[lo:hi], rtol=1e-5, atol=2e-6)
         for k, g in gP.items():
-            torch.testing.assert_close(g, P[k].grad, rtol=5e-5, atol=5e-6, msg=lambda m: k + m)  # cross-rank sum order
+            # weight gradients are fp32 sums over all edges, split differently across ranks
+            torch.testing.assert_close(g, P[k].grad, rtol=1e-4, atol=1e-5 * max(1.0, float(P[k].grad.abs().max())),
+                                       msg=lambda m: k + m)
