@@ -1,0 +1,80 @@
+"""2-GPU parity of the partitioned layer (NCCL all-gather / reduce-scatter) against the single-GPU layer.
+Skipped on a 1-GPU box; run with `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from tests._cases import make_graph
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, q):
+    import dualmessagepassing_b200 as dmp
+    from dualmessagepassing_b200.constants import REVFLAG
+    from dualmessagepassing_b200.parallel import PartitionedDMPLayer
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    n, h = 3000, 64
+    s, d, r = make_graph(seed=5, n=n, e0=20000, rev="halves", isolated=0)
+    E = len(s)
+    torch.manual_seed(2)
+    layer = dmp.DMPLayer(h, h, num_mlp_layers=2, batch_norm=False, act_func="leaky_relu").to(dev)
+    g = torch.Generator().manual_seed(3)
+    xv, xe = torch.randn(n, h, generator=g).to(dev), torch.randn(E, h, generator=g).to(dev)
+    gv, ge = torch.randn(n, h, generator=g).to(dev), torch.randn(E, h, generator=g).to(dev)
+    # single-GPU result on this rank
+    graph = dmp.DMPGraph(s, d, n, device=dev)
+    graph.edata[REVFLAG] = torch.from_numpy(r).to(dev)
+    a, b = xv.clone().requires_grad_(True), xe.clone().requires_grad_(True)
+    nv, ne = layer(graph, a, b)
+    torch.autograd.backward((nv, ne), (gv, ge))
+    ref_w = {k: p.grad.clone() for k, p in layer.named_parameters()}
+    layer.zero_grad()
+    # partitioned
+    runner = PartitionedDMPLayer(layer, s, d, r, n, rank, world, dev)
+    lo, hi = runner.n_lo, runner.n_hi
+    ids = torch.from_numpy(runner.part["eids"]).to(dev)
+    a2 = xv[lo:hi].clone().requires_grad_(True)
+    b2 = xe[ids].clone().requires_grad_(True)
+    nv2, ne2 = runner(a2, b2)
+    torch.autograd.backward((nv2, ne2), (gv[lo:hi], ge[ids]))
+    torch.cuda.synchronize()
+    ok = torch.equal(nv2, nv[lo:hi]) and torch.equal(ne2, ne[ids])  # same sums in the same order
+    msgs = []
+    if not ok:
+        msgs.append("forward differs: %g %g" % (float((nv2 - nv[lo:hi]).abs().max()), float((ne2 - ne[ids]).abs().max())))
+
+    def chk(name, x, y, rtol=1e-4, scale=1e-5):
+        atol = scale * max(1.0, float(y.abs().max()))
+        if not torch.allclose(x, y, rtol=rtol, atol=atol):
+            msgs.append("%s max abs diff %g" % (name, float((x - y).abs().max())))
+
+    chk("dXe", b2.grad, b.grad[ids])
+    chk("dXv", a2.grad, a.grad[lo:hi])
+    for k, p in layer.named_parameters():
+        chk(k, p.grad, ref_w[k])
+    q.put((rank, msgs))
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_partitioned_layer_matches_single_gpu_nccl():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = dict(q.get(timeout=300) for _ in range(2))
+    [p.join(timeout=60) for p in procs]
+    assert res == {0: [], 1: []}, res
