@@ -1,0 +1,394 @@
+// tf32x3_gemm.cu -- edge-sized projection GEMM on the 5th-gen tensor cores with fp32-level accuracy.
+//
+//   D[M,N] = epilogue( (row_scale ⊙ A)[M,K] · Bt[N,K]^T )          K, N in {64, 128}, M = number of edges/nodes
+//
+// Why: in strict fp32 the DMPNN layer is bound by its 15 edge-sized [E,H]x[H,H] projections (cuBLAS sgemm:
+// 48.7 TFLOP/s on B200, 5.4 ms per 8 M rows), not by the sparse core.  A single-pass TF32 GEMM is HBM-bound
+// (1.3 ms) but has 3e-4 error.  Here each fp32 operand is split as x = hi + lo with hi = tf32(x) and
+// three tcgen05.mma (kind::tf32) products hi·hi + lo·hi + hi·lo accumulate in fp32 in TMEM: measured error
+// vs fp64 equals cuBLAS sgemm's (~5e-7 max-norm relative), at tensor-core speed.
+//
+// Structure (one persistent CTA per SM, 13 warps, no TMA descriptors -- the operand transform needs the
+// data in registers anyway):
+//   warps 5..12  PRODUCERS  global fp32 (coalesced 128-bit, 3 k-blocks of loads in flight per thread)
+//                           -> optional row scale (fuses `coef ⊙ gE`, dmpnn.py:146 backward)
+//                           -> hi/lo split -> 128B-swizzled K-major smem tiles -> fence.proxy.async -> mbarrier
+//   warp  4      MMA        one elected lane issues 3 x (32/8) tcgen05.mma per k-block, tcgen05.commit
+//                           releases the smem stage / publishes the accumulator
+//   warps 0..3   EPILOGUE   tcgen05.ld 32x32b (thread = row) -> bias / activation / act' / accumulate -> global
+// The weight matrix (<= 64 KB) is split once per CTA and stays resident in smem; accumulators are double
+// buffered in TMEM (2 x N columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include "common.cuh"
+
+namespace dmp {
+namespace gemm {
+
+constexpr int kTileM = 128;
+constexpr int kKB = 32;                 // fp32 elements per k-block = one 128-byte swizzle row
+constexpr int kStages = 3;
+constexpr int kProducerWarps = 8;
+constexpr int kProducerThreads = kProducerWarps * 32;
+constexpr int kEpilogueWarps = 4;
+constexpr int kMmaWarp = 4;
+constexpr int kThreadsGemm = (kEpilogueWarps + 1 + kProducerWarps) * 32;  // 416
+constexpr int kPrefetch = 3;            // k-blocks of global loads kept in flight per producer thread
+
+// epilogue flags (low 4 bits = DMP_ACT_*)
+constexpr int kEpiMulActGradFromOutput = 32;  // D = acc * act'(aux) with aux = activation OUTPUT
+constexpr int kEpiAccumulate = 64;            // D += acc
+
+// ---- PTX wrappers ----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{ .reg .pred p; setp.ne.b32 p, %4, 0;\n"
+      "  tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p; }"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte swizzle: rows of 128 B, 8-row groups of 1024 B (SBO), descriptor version 1 (sm_100)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// kind::tf32, fp32 accumulate, A and B K-major, M = 128
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+}
+
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// byte offset of 16-byte chunk `c16` of row `r` inside a [rows x 128 B] swizzled block
+__device__ __forceinline__ uint32_t swz(int r, int c16) { return (uint32_t)(r * 128 + ((c16 ^ (r & 7)) << 4)); }
+
+__device__ __forceinline__ void split_store(uint32_t hi_addr, uint32_t lo_addr, float4 v) {
+  float4 h, l;
+  h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+  l.x = __fsub_rn(v.x, h.x); l.y = __fsub_rn(v.y, h.y); l.z = __fsub_rn(v.z, h.z); l.w = __fsub_rn(v.w, h.w);
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(hi_addr), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(lo_addr), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
+}
+
+struct GemmParams {
+  const float* A; int64_t lda;
+  const float* row_scale;
+  const float* Bt; int64_t ldb;
+  const float* bias;
+  const float* aux; int64_t ld_aux;
+  float* D; int64_t ldd;
+  int64_t M;
+  int epilogue;
+  float slope;
+};
+
+template <int N, int K>
+struct Smem {
+  static constexpr int kKBlocks = K / kKB;
+  static constexpr int kBBlockBytes = N * 128;                 // one k-block of B (hi or lo)
+  static constexpr int kBBytes = 2 * kKBlocks * kBBlockBytes;  // hi + lo
+  static constexpr int kABlockBytes = kTileM * 128;            // 16 KB
+  static constexpr int kStageBytes = 2 * kABlockBytes;         // hi + lo
+  static constexpr int kBarBytes = 256;
+  static constexpr int kTotal = kBBytes + kStages * kStageBytes + kBarBytes + 1024;  // + alignment slack
+};
+
+template <int N, int K>
+__global__ void __launch_bounds__(kThreadsGemm, 1) tf32x3_gemm_kernel(const GemmParams p) {
+  using L = Smem<N, K>;
+  constexpr int kKBlocks = L::kKBlocks;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sB = base;                                  // [hi kb0..][lo kb0..]
+  const uint32_t sA = base + L::kBBytes;                     // stage s: [hi 16K][lo 16K]
+  const uint32_t sBar = sA + kStages * L::kStageBytes;
+  const uint32_t bar_full = sBar;                            // kStages x 8 B
+  const uint32_t bar_empty = sBar + 8 * kStages;
+  const uint32_t bar_acc_full = sBar + 16 * kStages;         // 2 x 8 B
+  const uint32_t bar_acc_empty = bar_acc_full + 16;
+  const uint32_t tmem_slot = bar_acc_empty + 16;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t num_tiles = (p.M + kTileM - 1) / kTileM;
+
+  // ---- one-time setup: barriers, TMEM, resident split weights ---------------------------------------------
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(bar_full + 8 * s, kProducerThreads);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_acc_full + 8 * a, 1);
+      mbar_init(bar_acc_empty + 8 * a, kEpilogueWarps * 32);
+    }
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc(tmem_slot, 2 * N);
+  for (int c = threadIdx.x; c < N * (K / 4); c += kThreadsGemm) {  // 16-byte chunks of Bt[N,K]
+    const int n = c / (K / 4);
+    const int k4 = c % (K / 4);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p.Bt + (int64_t)n * p.ldb + k4 * 4));
+    const int kb = k4 / 8, c16 = k4 % 8;
+    const uint32_t off = (uint32_t)kb * L::kBBlockBytes + swz(n, c16);
+    split_store(sB + off, sB + kKBlocks * L::kBBlockBytes + off, v);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp > kMmaWarp) {
+    // =========================== PRODUCERS ===========================
+    const int pt = threadIdx.x - (kMmaWarp + 1) * 32;          // 0..255
+    // thread handles chunks c = pt + 256*i (i<4): row = c/8, 16B-chunk = c%8  (a warp covers 4 full rows)
+    const int c16 = pt & 7;
+    const int row0 = pt >> 3;                                   // rows row0 + 32*i
+    const int64_t total_kb = ((num_tiles - (int64_t)blockIdx.x + gridDim.x - 1) / gridDim.x) * kKBlocks;
+    float4 buf[kPrefetch][4];
+    float scale_buf[kPrefetch][4];
+    int64_t it_load = 0;
+    auto load_block = [&](int64_t it, float4 (&dst)[4], float (&sc)[4]) {
+      const int64_t tile = (int64_t)blockIdx.x + (it / kKBlocks) * gridDim.x;
+      const int kb = (int)(it % kKBlocks);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int64_t r = tile * kTileM + row0 + 32 * i;
+        if (r < p.M) {
+          const float* src = p.A + r * p.lda + kb * kKB + c16 * 4;
+          float4 v;
+          asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                       : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(src));
+          dst[i] = v;
+          sc[i] = p.row_scale != nullptr ? __ldg(p.row_scale + r) : 1.0f;
+        } else {
+          dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          sc[i] = 1.0f;
+        }
+      }
+    };
+#pragma unroll
+    for (int slot = 0; slot < kPrefetch; ++slot)
+      if (slot < total_kb) {
+        load_block(slot, buf[slot], scale_buf[slot]);
+        ++it_load;
+      }
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int64_t it0 = 0; it0 < total_kb; it0 += kPrefetch) {
+#pragma unroll
+      for (int slot = 0; slot < kPrefetch; ++slot) {  // compile-time slot: the prefetch buffers stay in registers
+        if (it0 + slot < total_kb) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          const uint32_t hi = sA + stage * L::kStageBytes;
+          const uint32_t lo = hi + L::kABlockBytes;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float4 v = buf[slot][i];
+            if (p.row_scale != nullptr) {
+              const float s = scale_buf[slot][i];
+              v.x = __fmul_rn(s, v.x); v.y = __fmul_rn(s, v.y); v.z = __fmul_rn(s, v.z); v.w = __fmul_rn(s, v.w);
+            }
+            const uint32_t off = swz(row0 + 32 * i, c16);
+            split_store(hi + off, lo + off, v);
+          }
+          fence_proxy_async();
+          mbar_arrive(bar_full + 8 * stage);
+          if (it_load < total_kb) {
+            load_block(it_load, buf[slot], scale_buf[slot]);
+            ++it_load;
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // =========================== MMA ISSUER ===========================
+    constexpr uint32_t idesc = make_idesc(N);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(bar_acc_empty + 8 * acc, acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N);
+      for (int kb = 0; kb < kKBlocks; ++kb) {
+        mbar_wait(bar_full + 8 * stage, phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_hi = sA + stage * L::kStageBytes;
+          const uint32_t a_lo = a_hi + L::kABlockBytes;
+          const uint32_t b_hi = sB + kb * L::kBBlockBytes;
+          const uint32_t b_lo = b_hi + kKBlocks * L::kBBlockBytes;
+#pragma unroll
+          for (int j = 0; j < kKB / 8; ++j) {
+            const uint64_t dah = make_smem_desc(a_hi + j * 32);
+            const uint64_t dal = make_smem_desc(a_lo + j * 32);
+            const uint64_t dbh = make_smem_desc(b_hi + j * 32);
+            const uint64_t dbl = make_smem_desc(b_lo + j * 32);
+            // small terms first, the dominant hi*hi product last
+            umma_tf32(d_tmem, dal, dbh, idesc, (kb | j) != 0 ? 1u : 0u);
+            umma_tf32(d_tmem, dah, dbl, idesc, 1u);
+            umma_tf32(d_tmem, dah, dbh, idesc, 1u);
+          }
+          umma_commit(bar_empty + 8 * stage);                 // smem stage free once these MMAs retire
+          if (kb == kKBlocks - 1) umma_commit(bar_acc_full + 8 * acc);
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // =========================== EPILOGUE ===========================
+    const int act = p.epilogue & 15;
+    const bool mul_grad = (p.epilogue & kEpiMulActGradFromOutput) != 0;
+    const bool accumulate = (p.epilogue & kEpiAccumulate) != 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(bar_acc_full + 8 * acc, acc_phase);
+      tc_fence_after();
+      const int64_t r = tile * kTileM + warp * 32 + lane;     // TMEM lane == tile row
+      const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * N);
+#pragma unroll 1
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        float v[32];
+        tmem_ld32(t_row + c0, v);
+        if (r < p.M) {
+          float* drow = p.D + r * p.ldd + c0;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            if (p.bias != nullptr) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + 4 * q));
+              o.x = __fadd_rn(o.x, b.x); o.y = __fadd_rn(o.y, b.y); o.z = __fadd_rn(o.z, b.z); o.w = __fadd_rn(o.w, b.w);
+            }
+            if (mul_grad) {
+              const float4 y = *reinterpret_cast<const float4*>(p.aux + r * p.ld_aux + c0 + 4 * q);
+              o.x = __fmul_rn(o.x, act_grad_from_output(y.x, act, p.slope));
+              o.y = __fmul_rn(o.y, act_grad_from_output(y.y, act, p.slope));
+              o.z = __fmul_rn(o.z, act_grad_from_output(y.z, act, p.slope));
+              o.w = __fmul_rn(o.w, act_grad_from_output(y.w, act, p.slope));
+            } else if (act != DMP_ACT_NONE) {
+              o.x = apply_act(o.x, act, p.slope); o.y = apply_act(o.y, act, p.slope);
+              o.z = apply_act(o.z, act, p.slope); o.w = apply_act(o.w, act, p.slope);
+            }
+            if (accumulate) {
+              const float4 d = *reinterpret_cast<const float4*>(drow + 4 * q);
+              o.x = __fadd_rn(d.x, o.x); o.y = __fadd_rn(d.y, o.y); o.z = __fadd_rn(d.z, o.z); o.w = __fadd_rn(d.w, o.w);
+            }
+            *reinterpret_cast<float4*>(drow + 4 * q) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_acc_empty + 8 * acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  // ---- teardown ---------------------------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, 2 * N);
+}
+
+template <int N, int K>
+static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
+  using L = Smem<N, K>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tf32x3_gemm_kernel<N, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    if (e != cudaSuccess) {
+      set_error("gemm_tf32x3: cannot reserve %d bytes of shared memory: %s", L::kTotal, cudaGetErrorString(e));
+      return DMP_ERR_CUDA;
+    }
+    configured = true;
+  }
+  const int64_t tiles = (p.M + kTileM - 1) / kTileM;
+  const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
+  tf32x3_gemm_kernel<N, K><<<grid, kThreadsGemm, L::kTotal, stream>>>(p);
+  return launch_status("tf32x3_gemm_kernel");
+}
+
+}  // namespace gemm
+}  // namespace dmp
+
+extern "C" int dmp_gemm_tf32x3(const float* A, int64_t lda, const float* row_scale, const float* Bt, int64_t ldb,
+                               const float* bias, const float* aux, int64_t ld_aux, float* D, int64_t ldd,
+                               int64_t M, int64_t N, int64_t K, int epilogue, float slope, void* stream) {
+  using namespace dmp;
+  using namespace dmp::gemm;
+  DMP_CHECK_ARG(M >= 0, "gemm_tf32x3: negative M");
+  if (M == 0) return DMP_OK;
+  DMP_CHECK_ARG(A && Bt && D, "gemm_tf32x3: null pointer");
+  DMP_CHECK_ARG((N == 64 || N == 128) && (K == 64 || K == 128), "gemm_tf32x3: N and K must be 64 or 128 (got %lld, %lld)",
+                (long long)N, (long long)K);
+  DMP_CHECK_ARG(lda >= K && ldb >= K && ldd >= N && lda % 4 == 0 && ldb % 4 == 0 && ldd % 4 == 0,
+                "gemm_tf32x3: leading dimensions must be >= the row length and multiples of 4");
+  DMP_CHECK_ARG(aligned_to(A, 16) && aligned_to(Bt, 16) && aligned_to(D, 16) && aligned_to(bias, 16) && aligned_to(aux, 16),
+                "gemm_tf32x3: operands must be 16-byte aligned");
+  const int act = epilogue & 15;
+  DMP_CHECK_ARG(act >= DMP_ACT_NONE && act <= DMP_ACT_SIGMOID, "gemm_tf32x3: bad activation");
+  DMP_CHECK_ARG(!(epilogue & kEpiMulActGradFromOutput) || (aux != nullptr && ld_aux >= N && ld_aux % 4 == 0),
+                "gemm_tf32x3: act' epilogue needs aux");
+  DMP_CHECK_ARG(A != D, "gemm_tf32x3: D must not alias A");
+  GemmParams p;
+  p.A = A; p.lda = lda; p.row_scale = row_scale; p.Bt = Bt; p.ldb = ldb; p.bias = bias;
+  p.aux = aux; p.ld_aux = ld_aux; p.D = D; p.ldd = ldd; p.M = M; p.epilogue = epilogue; p.slope = slope;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (N == 128 && K == 128) return launch_gemm<128, 128>(p, s);
+  if (N == 128 && K == 64) return launch_gemm<128, 64>(p, s);
+  if (N == 64 && K == 128) return launch_gemm<64, 128>(p, s);
+  return launch_gemm<64, 64>(p, s);
+}

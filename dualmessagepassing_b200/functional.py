@@ -187,3 +187,41 @@ def gate_residual(x, gate=None, prev=None, act="none", slope=0.0):
     if gate is not None and gate.requires_grad:
         raise NotImplementedError("gate_residual does not differentiate with respect to the gate")
     return _GateResidual.apply(x, gate, prev, _ACT_IDS[act], float(slope))
+
+
+def gemm_tf32x3_supported(M, N, K):
+    return N in (64, 128) and K in (64, 128)
+
+
+def gemm_tf32x3(A, Wt, *, row_scale=None, bias=None, act="none", slope=0.0, aux=None, mul_act_grad=False,
+                accumulate=False, out=None):
+    """D = epilogue((row_scale ⊙ A) @ Wt.T) on the tcgen05 tensor cores with a 3xTF32 split (fp32-level accuracy).
+
+    A [M,K] fp32 (dense rows), Wt [N,K] (nn.Linear layout).  Raw, non-differentiable (the fused layer calls it)."""
+    _lib.require_cuda(A, Wt, row_scale, bias, aux)
+    A, lda = _lib.row_major(A)
+    Wt, ldb = _lib.row_major(Wt)
+    M, K = A.shape
+    N = Wt.shape[0]
+    if Wt.shape[1] != K:
+        raise ValueError("inner dimensions differ: A is %s, Wt is %s" % (tuple(A.shape), tuple(Wt.shape)))
+    if out is None:
+        if accumulate:
+            raise ValueError("accumulate=True needs `out`")
+        out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    _, ldd = _lib.row_major(out)
+    epi = _ACT_IDS[act]
+    ld_aux = 0
+    if mul_act_grad:
+        aux, ld_aux = _lib.row_major(aux)
+        epi |= _lib.EPI_MUL_ACT_GRAD
+    if accumulate:
+        epi |= _lib.EPI_ACCUMULATE
+    if row_scale is not None:
+        row_scale = row_scale.reshape(-1).contiguous()
+    if bias is not None:
+        bias = bias.contiguous()
+    _lib.call("dmp_gemm_tf32x3", A.device, _lib.ptr(A), lda, _lib.ptr(row_scale), _lib.ptr(Wt), ldb,
+              _lib.ptr(bias), _lib.ptr(aux if mul_act_grad else None), ld_aux, _lib.ptr(out), ldd, M, N, K, epi,
+              float(slope), _stream(A), tag="gemm_tf32x3")
+    return out

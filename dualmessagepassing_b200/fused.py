@@ -16,7 +16,7 @@ Reference lines: SubgraphCountingMatching/models/dmpnn.py:111-156 (forward), SUR
 import torch
 
 from . import _lib
-from .functional import edge_backward, edge_update, segment_reduce
+from .functional import edge_backward, edge_update, gemm_tf32x3, segment_reduce
 
 _ACT = {"none": _lib.ACT_NONE, "relu": _lib.ACT_RELU, "leaky_relu": _lib.ACT_LEAKY_RELU,
         "tanh": _lib.ACT_TANH, "sigmoid": _lib.ACT_SIGMOID}
@@ -47,11 +47,45 @@ def _act_backward_inplace(g, y, act, slope):
     return g
 
 
+# Dense backend of the edge-/node-sized projections:
+#   "auto"    tcgen05 3xTF32 kernel (dmp_gemm_tf32x3, fp32-level accuracy) when N, K in {64,128}, else cuBLAS
+#   "cublas"  always torch.mm (cuBLAS sgemm)
+DENSE_BACKEND = "auto"
+_ACT_NAME = {v: k for k, v in _ACT.items()}
+
+
+def _use_tc(A, Wt):
+    return (DENSE_BACKEND == "auto" and A.dtype == torch.float32 and A.shape[0] > 0
+            and Wt.shape[0] in (64, 128) and Wt.shape[1] in (64, 128)
+            and A.stride(1) == 1 and A.stride(0) % 4 == 0 and A.data_ptr() % 16 == 0)
+
+
+def _rowmm(A, Wt, *, bias=None, act=_lib.ACT_NONE, slope=0.0, aux=None, mul_act_grad=False, accumulate=False,
+           out=None):
+    """out (+)= epilogue(A @ Wt.T); Wt is [N,K] (nn.Linear layout).  One launch on the tensor-core path."""
+    if _use_tc(A, Wt) and (out is None or (out.stride(1) == 1 and out.stride(0) % 4 == 0 and out.data_ptr() % 16 == 0)):
+        return gemm_tf32x3(A, Wt.contiguous(), bias=bias, act=_ACT_NAME[act], slope=slope, aux=aux,
+                           mul_act_grad=mul_act_grad, accumulate=accumulate, out=out)
+    if accumulate:
+        out.addmm_(A, Wt.t())
+        return out
+    if out is not None and bias is None and act == _lib.ACT_NONE and not mul_act_grad:
+        return torch.mm(A, Wt.t(), out=out)
+    r = torch.addmm(bias, A, Wt.t()) if bias is not None else torch.mm(A, Wt.t())
+    if mul_act_grad:
+        _act_backward_inplace(r, aux, act, slope)
+    else:
+        _act_inplace(r, act, slope)
+    if out is not None:
+        out.copy_(r)
+        return out
+    return r
+
+
 def _mlp_forward(pre, W1, b1, W2, b2, act, slope):
     """Linear -> act -> Linear (dmpnn.py:45-52 without BN). Returns (out, h1) with h1 = act(lin1)."""
-    h1 = torch.addmm(b1, pre, W1.t()) if b1 is not None else pre @ W1.t()
-    _act_inplace(h1, act, slope)
-    out = torch.addmm(b2, h1, W2.t()) if b2 is not None else h1 @ W2.t()
+    h1 = _rowmm(pre, W1, bias=b1, act=act, slope=slope)      # bias + activation in the GEMM epilogue
+    out = _rowmm(h1, W2, bias=b2)
     return out, h1
 
 
@@ -61,12 +95,12 @@ def _mlp_backward(g_out, pre, h1, W1, W2, act, slope, need_w):
     if need_w:
         dW2 = g_out.t() @ h1
         db2 = g_out.sum(0)
-    g1 = g_out @ W2                      # new edge-sized buffer
-    _act_backward_inplace(g1, h1, act, slope)
+    # g1 = (g_out @ W2) * act'(h1): new edge-sized buffer, act' folded into the GEMM epilogue
+    g1 = _rowmm(g_out, W2.t(), act=act, slope=slope, aux=h1, mul_act_grad=True)
     if need_w:
         dW1 = g1.t() @ pre
         db1 = g1.sum(0)
-    g_pre = torch.mm(g1, W1, out=h1)     # h1 is dead: re-use its storage
+    g_pre = _rowmm(g1, W1.t(), out=h1)   # h1 is dead: re-use its storage
     return g_pre, g1, dW1, db1, dW2, db2
 
 
@@ -89,26 +123,30 @@ class _FusedDMPLayer(torch.autograd.Function):
             csc_indptr = plan.csc_indptr[n_lo:n_hi + 1]
 
         # ---- node side (dmpnn.py:113-133): project, aggregate incident edge messages, self loop, bias
-        Ln = X_v @ nloop_w
+        Ln = _rowmm(X_v, nloop_w.t())
+        in_t, out_t = in_w.t(), out_w.t()
         if plan.rev_layout == "none":
-            M, m_off = X_e @ in_w, 0
+            M, m_off = _rowmm(X_e, in_t), 0
         elif plan.rev_layout == "halves":
             h = E // 2
             M, m_off = torch.empty((E, H), dtype=X_e.dtype, device=X_e.device), 0
-            torch.mm(X_e[:h], in_w, out=M[:h])
-            torch.mm(X_e[h:], out_w, out=M[h:])
+            _rowmm(X_e[:h], in_t, out=M[:h])
+            _rowmm(X_e[h:], out_t, out=M[h:])
         else:
-            M, m_off = X_e @ torch.cat([in_w, out_w], dim=1), H
+            # two-branch buffer [E, 2H]: both projections, the kernel picks the half by the edge's flag
+            M, m_off = torch.empty((E, 2 * H), dtype=X_e.dtype, device=X_e.device), H
+            _rowmm(X_e, in_t, out=M[:, :H])
+            _rowmm(X_e, out_t, out=M[:, H:])
         node_pre = segment_reduce(csc_indptr, plan.csc_eid, M, H, w_perm=norm_perm, rev_col_offset=m_off,
                                   base=Ln, bias=nbias, mode=_lib.SEG_SIGN_BY_REV, out=Ln,
                                   tag="segment_reduce.node_fwd")
         del M
 
         # ---- edge side (dmpnn.py:112-123,142-149): endpoint gather, degree term, self loop, bias
-        Qd = X_v_full @ dst_w
-        Qs = X_v_full @ src_w
-        P = X_e @ (src_w - dst_w)
-        S = X_e @ eloop_w
+        Qd = _rowmm(X_v_full, dst_w.t())
+        Qs = _rowmm(X_v_full, src_w.t())
+        P = _rowmm(X_e, (src_w - dst_w).t())
+        S = _rowmm(X_e, eloop_w.t())
         edge_pre = edge_update(plan, S, P, Qd, Qs, ebias, order, out=S)
         del P, Qd, Qs
 
@@ -186,27 +224,28 @@ class _FusedDMPLayer(torch.autograd.Function):
         dX_v = dX_e = None
         if need_xv:
             if part is None:
-                dX_v = gN @ nloop_w.t()
-                dX_v.addmm_(dQd, dst_w.t())
-                dX_v.addmm_(dQs, src_w.t())
+                dX_v = _rowmm(gN, nloop_w)
+                _rowmm(dQd, dst_w, out=dX_v, accumulate=True)
+                _rowmm(dQs, src_w, out=dX_v, accumulate=True)
             else:
                 # partial sums over this rank's edges for EVERY node -> owners (reduce-scatter over NVLink)
-                partial = dQd @ dst_w.t()
-                partial.addmm_(dQs, src_w.t())
+                partial = _rowmm(dQd, dst_w)
+                _rowmm(dQs, src_w, out=partial, accumulate=True)
                 dX_v = reduce_scatter_rows(partial, group)
-                dX_v.addmm_(gN, nloop_w.t())
+                _rowmm(gN, nloop_w, out=dX_v, accumulate=True)
                 del partial
         if need_xe:
-            dX_e = gE @ eloop_w.t()
-            dX_e.addmm_(CG, w_sd.t())
+            dX_e = _rowmm(gE, eloop_w)
+            _rowmm(CG, w_sd, out=dX_e, accumulate=True)
             if plan.rev_layout == "none":
-                dX_e.addmm_(T, in_w.t())
+                _rowmm(T, in_w, out=dX_e, accumulate=True)
             elif plan.rev_layout == "halves":
                 h = E // 2
-                dX_e[:h].addmm_(T[:h], in_w.t())
-                dX_e[h:].addmm_(T[h:], out_w.t())
+                _rowmm(T[:h], in_w, out=dX_e[:h], accumulate=True)
+                _rowmm(T[h:], out_w, out=dX_e[h:], accumulate=True)
             else:
-                dX_e.addmm_(T, torch.cat([in_w, out_w], dim=1).t())
+                _rowmm(T[:, :H], in_w, out=dX_e, accumulate=True)
+                _rowmm(T[:, H:], out_w, out=dX_e, accumulate=True)
         d_in = d_out = d_src = d_dst = d_nloop = d_eloop = d_nb = d_eb = None
         if need_w:
             d_nloop = X_v.t() @ gN

@@ -158,6 +158,23 @@ DMP_API int dmp_gate_residual_backward(const float* gout, int64_t ld_gout, const
                                const float* gate, float* gx, int64_t ld_gx, int64_t rows, int64_t H,
                                int act, float slope, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Edge-sized projection on the tcgen05 tensor cores with fp32-level accuracy (3xTF32 split):
+ *
+ *   D[M,N] = epilogue( (row_scale ⊙ A)[M,K] · Bt[N,K]^T )        N, K in {64,128}; Bt is the weight in
+ *                                                                 nn.Linear layout ([out, in], row-major)
+ * Replaces the per-edge `th.matmul(...)` calls of dmpnn.py:112-113,120-121,146-147 and the MLP Linears
+ * (dmpnn.py:45-52) and their autograd transposes.  row_scale [M] (may be NULL) multiplies each row of A
+ * first, as a separately rounded fp32 product (fuses `coef ⊙ gE`).  epilogue = DMP_ACT_* id, optionally
+ * OR-ed with DMP_EPI_MUL_ACT_GRAD (D = acc * act'(aux), aux = activation OUTPUT [M,N]) and/or
+ * DMP_EPI_ACCUMULATE (D += result).  bias [N] may be NULL.  D must not alias A.
+ */
+#define DMP_EPI_MUL_ACT_GRAD 32
+#define DMP_EPI_ACCUMULATE 64
+DMP_API int dmp_gemm_tf32x3(const float* A, int64_t lda, const float* row_scale, const float* Bt, int64_t ldb,
+                            const float* bias, const float* aux, int64_t ld_aux, float* D, int64_t ldd,
+                            int64_t M, int64_t N, int64_t K, int epilogue, float slope, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,85 @@
+"""tcgen05 3xTF32 projection GEMM (dmp_gemm_tf32x3) against fp64 and against cuBLAS sgemm.
+
+Floating point: the bar is fp32-level accuracy -- max-norm relative error vs an fp64 product <= 2.5e-6 (north_star
+tolerance is rel 1e-5) and within 4x of cuBLAS sgemm's own error (+5e-7): measured 1.2e-6 vs 5.7e-7, the tensor
+core's fp32 accumulator truncates where SIMT FMA rounds.  Epilogues are compared with torch fp32 ops."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _err(x, ref):
+    return float((x.double() - ref).abs().max() / ref.abs().max())
+
+
+@pytest.mark.parametrize("M", [1, 127, 128, 129, 1000, 148 * 128 + 5, 300_000])
+@pytest.mark.parametrize("N,K", [(128, 128), (64, 64), (128, 64), (64, 128)])
+def test_gemm_matches_fp64(M, N, K):
+    from dualmessagepassing_b200 import functional as F
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    Wt = torch.randn(N, K, device="cuda", generator=g) / 4
+    ref = A.double() @ Wt.double().t()
+    got = F.gemm_tf32x3(A, Wt)
+    e_ours, e_cublas = _err(got, ref), _err(A @ Wt.t(), ref)
+    assert e_ours <= 2.5e-6, e_ours
+    assert e_ours <= 4 * e_cublas + 5e-7, (e_ours, e_cublas)
+
+
+def test_gemm_wide_dynamic_range_and_special_values():
+    from dualmessagepassing_b200 import functional as F
+    g = torch.Generator(device="cuda").manual_seed(0)
+    A = torch.randn(5000, 128, device="cuda", generator=g) * torch.logspace(-6, 6, 128, device="cuda")
+    A[7] = 0.0
+    Wt = torch.randn(128, 128, device="cuda", generator=g)
+    ref = A.double() @ Wt.double().t()
+    got = F.gemm_tf32x3(A, Wt)
+    rowscale = ref.abs().max(dim=1, keepdim=True).values.clamp_min(1e-30)
+    assert float(((got.double() - ref).abs() / rowscale).max()) <= 2.5e-6
+    assert torch.all(got[7] == 0)
+
+
+@pytest.mark.parametrize("act,slope", [("none", 0.0), ("relu", 0.0), ("leaky_relu", 1 / 5.5), ("tanh", 0.0)])
+def test_gemm_epilogues(act, slope):
+    from dualmessagepassing_b200 import functional as F
+    g = torch.Generator(device="cuda").manual_seed(1)
+    M, N, K = 3001, 128, 128
+    A = torch.randn(M, K, device="cuda", generator=g)
+    Wt = torch.randn(N, K, device="cuda", generator=g) / 4
+    bias = torch.randn(N, device="cuda", generator=g)
+    scale = torch.rand(M, device="cuda", generator=g) * 10
+    plain = F.gemm_tf32x3(A, Wt)
+    fn = {"none": lambda x: x, "relu": torch.relu, "tanh": torch.tanh,
+          "leaky_relu": lambda x: torch.nn.functional.leaky_relu(x, slope)}[act]
+    # bias + activation: same accumulator, then the same fp32 ops as torch
+    got = F.gemm_tf32x3(A, Wt, bias=bias, act=act, slope=slope)
+    torch.testing.assert_close(got, fn(plain + bias), rtol=1e-6, atol=1e-6)
+    # row scale is applied to A as an individually rounded fp32 product
+    got = F.gemm_tf32x3(A, Wt, row_scale=scale)
+    assert torch.equal(got, F.gemm_tf32x3(scale.unsqueeze(1) * A, Wt))
+    # accumulate into an existing D
+    D0 = torch.randn(M, N, device="cuda", generator=g)
+    D = D0.clone()
+    F.gemm_tf32x3(A, Wt, out=D, accumulate=True)
+    assert torch.equal(D, D0 + plain)
+    # act'(output) multiply (MLP backward)
+    y = fn(torch.randn(M, N, device="cuda", generator=g))
+    got = F.gemm_tf32x3(A, Wt, act=act, slope=slope, aux=y, mul_act_grad=True)
+    grad = {"none": torch.ones_like(y), "relu": (y > 0).float(), "tanh": 1 - y * y,
+            "leaky_relu": torch.where(y > 0, torch.ones_like(y), torch.full_like(y, slope))}[act]
+    torch.testing.assert_close(got, plain * grad, rtol=1e-6, atol=1e-6)
+
+
+def test_gemm_strided_and_deterministic():
+    from dualmessagepassing_b200 import functional as F
+    g = torch.Generator(device="cuda").manual_seed(2)
+    big = torch.randn(4000, 256, device="cuda", generator=g)
+    A = big[:, 128:]                      # lda = 256
+    Wt = torch.randn(128, 128, device="cuda", generator=g)
+    out = torch.zeros(4000, 256, device="cuda")
+    F.gemm_tf32x3(A, Wt, out=out[:, :128])  # ldd = 256
+    ref = A.contiguous().double() @ Wt.double().t()
+    assert _err(out[:, :128], ref) <= 2.5e-6 and torch.all(out[:, 128:] == 0)
+    again = F.gemm_tf32x3(A, Wt)
+    assert torch.equal(again, out[:, :128])
