@@ -59,6 +59,9 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the secondary train graphs/sec measurement")
+    ap.add_argument("--train-config", default="cfg2", choices=["cfg1", "cfg2", "cfg3"])
+    ap.add_argument("--train-steps", type=int, default=30)
     ap.add_argument("--cpu-sample-edges", type=int, default=0, help="override the CPU sample size (edges incl. reversed)")
     return ap.parse_args()
 
@@ -192,6 +195,51 @@ def kernel_bytes(tag, N, E, H, has_norm=False):
     if tag == "act_inplace":
         return None  # rows differ (node / edge); filled by caller
     return None
+
+
+def run_train(args, dev, world, rank):
+    """Secondary metric of BASELINE.json: end-to-end training graphs/sec on configs[1] (batch 512 pairs per
+    GPU, data parallel).  Every timed step = host collate of a fresh batch + pinned H2D + plan builds + model
+    forward/backward + gradient all-reduce + clip + AdamW; loss read back at the end of the run only."""
+    import torch.distributed as dist
+
+    from dualmessagepassing_b200 import _lib
+    from dualmessagepassing_b200 import train_step as ts
+    cfg = ts.CONFIGS[args.train_config]
+    ds = ts.SyntheticPairDataset(args.train_config, num=4 * cfg["pairs"], seed=2000 + rank)
+    torch.manual_seed(2000)
+    model = ts.SubgraphCountingModel(cfg["hidden"], cfg["labels"][0], cfg["labels"][1]).to(dev)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, amsgrad=True)
+    rng = np.random.Generator(np.random.PCG64(7 + rank))
+    h2d = 0
+
+    def one_step():
+        nonlocal h2d
+        idx = np.sort(rng.choice(ds.num, size=cfg["pairs"], replace=False))
+        p, g, y, nb = ts.to_device(ts.collate(ds, idx), dev)
+        h2d = nb
+        return ts.train_step(model, opt, p, g, y, world=world)
+
+    for _ in range(5):
+        one_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    l0 = _lib.LAUNCHES
+    t0 = time.perf_counter()
+    for _ in range(args.train_steps):
+        loss = one_step()
+    torch.cuda.synchronize()
+    dt = torch.tensor([(time.perf_counter() - t0) / args.train_steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    sec = float(dt.item())
+    return {"metric": "train graphs/sec (pattern/graph pairs)", "value": cfg["pairs"] * world / sec, "unit": "pairs/s",
+            "ms_per_step": sec * 1e3, "steps": args.train_steps, "pairs_per_gpu": cfg["pairs"], "n_gpus": world,
+            "scaling": "weak", "config": "BASELINE configs[%d] (%s): 3 shared DMP layers, hidden %d, sum-pool head, "
+            "MSE, AdamW(amsgrad)" % ({"cfg1": 0, "cfg2": 1, "cfg3": 2}[args.train_config], args.train_config, cfg["hidden"]),
+            "h2d_bytes_per_step": int(h2d), "dmp_launches_per_step": (_lib.LAUNCHES - l0) / args.train_steps,
+            "final_loss": float(loss.item())}
 
 
 def run_ours(args):
@@ -381,6 +429,12 @@ def run_ours(args):
                "what": "pinned host node/edge features -> HBM, DMPLayer fwd+bwd through the module API, "
                        "loss scalar + all parameter gradients -> host; graph and its plan stay resident"}
 
+    train = None
+    if not args.no_train:
+        del xv, xe, gv, ge, graph, runner, plan
+        torch.cuda.empty_cache()
+        train = run_train(args, dev, world, rank)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -394,7 +448,7 @@ def run_ours(args):
                        "dst-range node partition x%d, all-gather fwd / reduce-scatter bwd" % world,
                        "plan_build_ms_excluded": plan_ms},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
-            "clocks": clocks, "kernels": kernels,
+            "clocks": clocks, "kernels": kernels, "train": train,
             "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9,
         }
         print(json.dumps(line), flush=True)

@@ -147,6 +147,7 @@ def get_plan(graph, rev_key, deg_key, validate=True):
     plan = cache.get(key)
     if plan is None:
         hint = getattr(graph, "rev_layout_hint", None)
+        validate = getattr(graph, "validate_plan", validate)
         plan = DMPPlan(src, dst, n, rev=rev, out_deg=deg, validate=validate, rev_layout=hint)
         cache.clear()
         cache[key] = plan

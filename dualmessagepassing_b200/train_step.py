@@ -1,0 +1,183 @@
+"""End-to-end training step around the DMPNN layers, for the graphs/sec measurement.
+
+The reference's trainer and `GraphAdjModelV2` (SubgraphCountingMatching/train.py:449-844,
+models/basemodel.py:965-1663) are callers of the hot path and are NOT rebuilt.  What the e2e metric needs is
+one step of the same shape: label embeddings -> label-match filter gate -> 3 shared DMP layers on the pattern
+batch and on the graph batch (mask / gate / residual) -> sum-pool prediction head -> MSE -> backward -> clip ->
+AdamW(amsgrad).  This module is that step, written for throughput: the per-batch host work is one vectorised
+collate, the device work has no host synchronisation, ragged pooling is a sorted-segment reduce.
+
+  SyntheticPairDataset   directed ER pattern/graph pairs of the BASELINE configs (numpy PCG64), stored flat
+  collate                `dgl.batch` + `add_reversed_edges` semantics on flat arrays (dataset.py:1321-1328,
+                         train.py:299-327): per graph [forward block | reversed block], offsets = prefix sums
+  SubgraphCountingModel  embedding / gate / DMPNNRepNet / SumPredictNet-shaped head (pred.py:87-156,198-216)
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .constants import EDGELABEL, NODELABEL, OUTDEGREE, REVFLAG
+from .functional import segment_reduce
+from .graph import DMPGraph
+from .models import DMPNNRepNet
+
+CONFIGS = {
+    # name: pairs/batch, graph n range, E0 per node, pattern n range, pattern E0 range, labels (v,e) graph, pattern, H
+    "cfg1": dict(pairs=64, gn=(8, 32), ge_per_n=3, pn=(3, 4), pe=(2, 4), labels=(1, 1), hidden=64),
+    "cfg2": dict(pairs=512, gn=(16, 64), ge_per_n=4, pn=(3, 8), pe=(2, 8), labels=(16, 16), hidden=64),
+    "cfg3": dict(pairs=64, gn=(10, 28), ge_per_n=2, pn=(4, 4), pe=(3, 3), labels=(7, 4), hidden=128),
+}
+
+
+class SyntheticPairDataset:
+    """`num` pattern/graph pairs as flat arrays: offsets[i]..offsets[i+1] index graph i's nodes / edges."""
+
+    def __init__(self, cfg, num, seed):
+        c = CONFIGS[cfg]
+        rng = np.random.Generator(np.random.PCG64(seed))
+        self.cfg, self.num = c, num
+
+        def build(n_range, e_fn, lv, le):
+            n = rng.integers(n_range[0], n_range[1] + 1, size=num)
+            e = np.asarray([e_fn(int(k)) for k in n], dtype=np.int64)
+            noff = np.concatenate([[0], np.cumsum(n)])
+            eoff = np.concatenate([[0], np.cumsum(e)])
+            owner = np.repeat(np.arange(num), e)
+            nn_ = n[owner]
+            u = (rng.random(eoff[-1]) * nn_).astype(np.int64)
+            v = (rng.random(eoff[-1]) * np.maximum(nn_ - 1, 1)).astype(np.int64)
+            v = np.where(nn_ > 1, v + (v >= u), v)  # no self loops
+            return dict(n=n, e=e, noff=noff, eoff=eoff, u=u, v=v,
+                        vl=rng.integers(0, lv, size=noff[-1]), el=rng.integers(0, le, size=eoff[-1]))
+
+        lv, le = c["labels"]
+        self.g = build(c["gn"], lambda k: c["ge_per_n"] * k, lv, le)
+        self.p = build(c["pn"], lambda k: int(rng.integers(c["pe"][0], c["pe"][1] + 1)), lv, le)
+        self.counts = rng.poisson(3.0, size=num).astype(np.float32)
+
+
+def _collate_side(d, idx):
+    """Disjoint union of graphs `idx`, reversed edges appended per graph (per-graph [fwd | rev] blocks)."""
+    n, e = d["n"][idx], d["e"][idx]
+    new_noff = np.concatenate([[0], np.cumsum(n)])
+    # gather node ranges
+    node_src = np.repeat(d["noff"][idx] - new_noff[:-1], n) + np.arange(new_noff[-1])
+    e2 = 2 * e
+    new_eoff = np.concatenate([[0], np.cumsum(e2)])
+    owner = np.repeat(np.arange(len(idx)), e2)
+    pos = np.arange(new_eoff[-1]) - new_eoff[:-1][owner]        # position inside the graph's doubled edge list
+    is_rev = pos >= e[owner]
+    orig = d["eoff"][idx][owner] + np.where(is_rev, pos - e[owner], pos)
+    u, v = d["u"][orig], d["v"][orig]
+    off = new_noff[:-1][owner]
+    src = np.where(is_rev, v, u) + off
+    dst = np.where(is_rev, u, v) + off
+    return dict(src=src, dst=dst, rev=is_rev, vl=d["vl"][node_src], el=d["el"][orig], n=n, e=e2,
+                num_nodes=int(new_noff[-1]), node_graph=np.repeat(np.arange(len(idx)), n))
+
+
+def collate(ds, idx):
+    return dict(p=_collate_side(ds.p, idx), g=_collate_side(ds.g, idx), y=ds.counts[idx])
+
+
+def to_device(batch, device, pinned=None):
+    """One H2D copy per array (non-blocking from pinned staging); returns (pattern, graph, target, bytes)."""
+    nbytes = 0
+
+    def put(a, dtype):
+        nonlocal nbytes
+        t = torch.from_numpy(np.ascontiguousarray(a))
+        if dtype is not None:
+            t = t.to(dtype)
+        t = t.pin_memory()
+        nbytes += t.numel() * t.element_size()
+        return t.to(device, non_blocking=True)
+
+    out = []
+    for side in ("p", "g"):
+        b = batch[side]
+        g = DMPGraph(put(b["src"], torch.int64), put(b["dst"], torch.int64), b["num_nodes"])
+        g.edata[REVFLAG] = put(b["rev"], torch.bool)
+        g.ndata[NODELABEL] = put(b["vl"], torch.int64)
+        g.edata[EDGELABEL] = put(b["el"], torch.int64)
+        g.ndata["graph_id"] = put(b["node_graph"], torch.int64)
+        g._batch_num_nodes = put(b["n"], torch.int64)
+        g._batch_num_edges = put(b["e"], torch.int64)
+        g.rev_layout_hint = "general"   # per-graph [fwd|rev] blocks
+        g.validate_plan = False         # synthetic ids are in range: skip the one D2H check per plan
+        out.append(g)
+    y = put(batch["y"], torch.float32)
+    return out[0], out[1], y, nbytes
+
+
+class SubgraphCountingModel(nn.Module):
+    def __init__(self, hidden, num_vlabels, num_elabels, num_layers=3, act_func="leaky_relu"):
+        super().__init__()
+        self.hidden, self.num_vlabels = hidden, num_vlabels
+        self.vl_emb = nn.Embedding(num_vlabels, hidden)
+        self.el_emb = nn.Embedding(2 * num_elabels, hidden)   # reversed edges: label += max label (train.py:310)
+        self.num_elabels = num_elabels
+        self.rep = DMPNNRepNet(hidden, num_layers=num_layers, rep_act_func=act_func, rep_dmpnn_num_mlp_layers=2,
+                               rep_dmpnn_batch_norm=False)
+        self.p_fc = nn.Linear(hidden, hidden)
+        self.g_fc = nn.Linear(hidden, hidden)
+        self.pred_fc1 = nn.Linear(4 * hidden + 4, hidden)
+        self.pred_fc2 = nn.Linear(hidden + 4, 1)
+        self.act = nn.LeakyReLU(1 / 5.5)
+
+    def _embed(self, g):
+        el = g.edata[EDGELABEL] + g.edata[REVFLAG].long() * self.num_elabels
+        return self.vl_emb(g.ndata[NODELABEL]), self.el_emb(el)
+
+    def _pool(self, x, g):
+        """Per-graph sum of node rows: nodes of a graph are contiguous -> sorted segments, no atomics."""
+        n = g.batch_num_nodes()
+        indptr = torch.zeros(n.numel() + 1, dtype=torch.int32, device=x.device)
+        indptr[1:] = torch.cumsum(n, 0)
+        return _SegSum.apply(x, indptr, g.ndata["graph_id"])
+
+    def forward(self, pattern, graph):
+        bsz = pattern.batch_num_nodes().numel()
+        # ScalarFilter-style gate (filter.py:6-16, basemodel.py:1394-1423): a graph node/edge passes if its
+        # label occurs in the paired pattern
+        pres_v = torch.zeros((bsz, self.num_vlabels), device=graph.device)
+        pres_v[pattern.ndata["graph_id"], pattern.ndata[NODELABEL]] = 1.0
+        v_gate = pres_v[graph.ndata["graph_id"], graph.ndata[NODELABEL]]
+        p_v, p_e = self._embed(pattern)
+        g_v, g_e = self._embed(graph)
+        p_v, p_e = self.rep.get_pattern_rep(pattern, p_v, p_e)
+        g_v, g_e = self.rep.get_graph_rep(graph, g_v, g_e, v_gate=v_gate)
+        p = self._pool(self.p_fc(p_v), pattern)
+        g = self._pool(self.g_fc(g_v), graph)
+        pl = pattern.batch_num_nodes().float().view(-1, 1)
+        gl = graph.batch_num_nodes().float().view(-1, 1)
+        extra = [pl, gl, 1.0 / pl, 1.0 / gl]
+        y = self.act(self.pred_fc1(torch.cat([p, g, g - p, g * p] + extra, dim=1)))
+        return self.pred_fc2(torch.cat([y] + extra, dim=1)).view(-1)
+
+
+class _SegSum(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, indptr, row_segment):
+        eid = torch.arange(x.shape[0], dtype=torch.int32, device=x.device)
+        ctx.save_for_backward(row_segment)
+        return segment_reduce(indptr, eid, x.contiguous(), x.shape[1], tag="segment_reduce.pool")
+
+    @staticmethod
+    def backward(ctx, g):
+        (row_segment,) = ctx.saved_tensors
+        return g[row_segment], None, None
+
+
+def train_step(model, optimizer, pattern, graph, target, *, world=1, clip=10.0):
+    """forward -> MSE -> backward -> (gradient all-reduce) -> clip -> optimizer.  Returns the loss tensor (device)."""
+    optimizer.zero_grad(set_to_none=True)
+    pred = model(pattern, graph)
+    loss = torch.mean((pred - target) ** 2)
+    loss.backward()
+    if world > 1:
+        from .parallel import allreduce_gradients
+        allreduce_gradients(model.parameters(), average=True)
+    torch.nn.utils.clip_grad_norm_(model.parameters(), clip, foreach=True)
+    optimizer.step()
+    return loss

@@ -162,10 +162,10 @@ def test_dmplayer_error_vs_fp64_not_worse_than_reference_fp32(n, e0, h, rev):
         err_ours = float((got - v64).abs().max()) / scale
         err_ref = float((ref32[k].double() - v64).abs().max()) / scale
         assert err_ours <= 1e-5, "%s: max-norm relative error %.3g" % (k, err_ours)
-        # outputs / input gradients: within 2x of the reference's own fp32 error.  Weight gradients are
-        # K = E long reductions where cuBLAS and MKL split K differently: allow 4x + 1e-6 (still ~1e-6 overall)
-        factor, slack = (4.0, 1e-6) if k.startswith("grad ") and "feat" not in k else (2.0, 2e-7)
-        assert err_ours <= factor * err_ref + slack, "%s: ours %.3g vs reference-fp32 %.3g" % (k, err_ours, err_ref)
+        # yardstick: the reference-order fp32 evaluation's own error.  The projections run on the tensor cores
+        # (3xTF32, measured 1.2e-6 per GEMM vs 5e-7 for sgemm) and weight gradients are K = E long reductions
+        # that cuBLAS and MKL split differently: allow 4x the reference error + 1e-6 (i.e. ~1e-6 .. 3e-6 overall)
+        assert err_ours <= 4.0 * err_ref + 1e-6, "%s: ours %.3g vs reference-fp32 %.3g" % (k, err_ours, err_ref)
 
 
 def test_layer_is_run_to_run_deterministic():
@@ -209,6 +209,9 @@ def test_fused_layer_equals_composed_path(mlp, act, rev):
         g.edata[REVFLAG] = torch.from_numpy(r).cuda()
     xv, xe = torch.randn(400, 64, device="cuda"), torch.randn(len(s), 64, device="cuda")
     gv, ge = torch.randn(400, 64, device="cuda"), torch.randn(len(s), 64, device="cuda")
+    from dualmessagepassing_b200 import fused as fused_mod
+    monkey = fused_mod.DENSE_BACKEND
+    fused_mod.DENSE_BACKEND = "cublas"  # same GEMM backend on both paths -> forward must be bit-identical
     res = {}
     for fused in (True, False):
         layer.fused = fused
@@ -218,7 +221,18 @@ def test_fused_layer_equals_composed_path(mlp, act, rev):
         torch.autograd.backward((nv, ne), (gv, ge))
         res[fused] = [nv.detach(), ne.detach(), a.grad, b.grad] + [
             p.grad.clone() if p.grad is not None else torch.zeros_like(p) for p in layer.parameters()]
+    fused_mod.DENSE_BACKEND = monkey
+    # third run: fused path with the tensor-core (3xTF32) projections, compared at fp32 tolerance
+    layer.fused = True
+    layer.zero_grad()
+    a, b = xv.clone().requires_grad_(True), xe.clone().requires_grad_(True)
+    nv, ne = layer(g, a, b)
+    torch.autograd.backward((nv, ne), (gv, ge))
+    tc = [nv.detach(), ne.detach(), a.grad, b.grad] + [
+        p.grad.clone() if p.grad is not None else torch.zeros_like(p) for p in layer.parameters()]
     names = ["node_out", "edge_out", "dXv", "dXe"] + [k for k, _ in layer.named_parameters()]
+    for k, x, y in zip(names, tc, res[False]):
+        torch.testing.assert_close(x, y, rtol=2e-5, atol=2e-5 * max(1.0, float(y.abs().max())), msg=lambda m: "tc " + k + m)
     for k, x, y in zip(names, res[True], res[False]):
         if k in ("node_out", "edge_out") and act in ("leaky_relu", "relu", "none"):
             assert torch.equal(x, y), k
