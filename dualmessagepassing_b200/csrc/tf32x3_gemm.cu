@@ -8,14 +8,17 @@
 // three tcgen05.mma (kind::tf32) products hi·hi + lo·hi + hi·lo accumulate in fp32 in TMEM: measured error
 // vs fp64 equals cuBLAS sgemm's (~5e-7 max-norm relative), at tensor-core speed.
 //
-// Structure (one persistent CTA per SM, 13 warps, no TMA descriptors -- the operand transform needs the
+// Structure (one persistent CTA per SM, 17 warps, no TMA descriptors -- the operand transform needs the
 // data in registers anyway):
-//   warps 5..12  PRODUCERS  global fp32 (coalesced 128-bit, 3 k-blocks of loads in flight per thread)
+//   warps 9..16  PRODUCERS  global fp32 (coalesced 128-bit, 3 k-blocks of loads in flight per thread)
 //                           -> optional row scale (fuses `coef ⊙ gE`, dmpnn.py:146 backward)
 //                           -> hi/lo split -> 128B-swizzled K-major smem tiles -> fence.proxy.async -> mbarrier
-//   warp  4      MMA        one elected lane issues 3 x (32/8) tcgen05.mma per k-block, tcgen05.commit
+//   warp  8      MMA        one elected lane issues 3 x (32/8) tcgen05.mma per k-block, tcgen05.commit
 //                           releases the smem stage / publishes the accumulator
-//   warps 0..3   EPILOGUE   tcgen05.ld 32x32b (thread = row) -> bias / activation / act' / accumulate -> global
+//   warps 0..7   EPILOGUE   tcgen05.ld 32x32b -> bias / activation / act' / accumulate -> global.  For N = 128 the
+//                           MMA is issued TRANSPOSED (weights as the M=128 operand, the edge tile as the N operand) so
+//                           that a TMEM lane is an output FEATURE: the 32 lanes of a warp then store 32 consecutive
+//                           floats of one output row (one 128-byte wavefront per store instead of 32)
 // The weight matrix (<= 64 KB) is split once per CTA and stays resident in smem; accumulators are double
 // buffered in TMEM (2 x N columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "common.cuh"
@@ -28,9 +31,9 @@ constexpr int kKB = 32;                 // fp32 elements per k-block = one 128-b
 constexpr int kStages = 3;
 constexpr int kProducerWarps = 8;
 constexpr int kProducerThreads = kProducerWarps * 32;
-constexpr int kEpilogueWarps = 4;
-constexpr int kMmaWarp = 4;
-constexpr int kThreadsGemm = (kEpilogueWarps + 1 + kProducerWarps) * 32;  // 416
+constexpr int kEpilogueWarps = 8;        // two warps per TMEM lane quadrant, each takes half of the columns
+constexpr int kMmaWarp = 8;
+constexpr int kThreadsGemm = (kEpilogueWarps + 1 + kProducerWarps) * 32;  // 544
 constexpr int kPrefetch = 3;            // k-blocks of global loads kept in flight per producer thread
 
 // epilogue flags (low 4 bits = DMP_ACT_*)
@@ -51,6 +54,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   do {
     asm volatile(
         "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {  // non-suspending poll
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   } while (!ok);
 }
@@ -89,14 +100,34 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // K-major, 128-byte swizzle: rows of 128 B, 8-row groups of 1024 B (SBO), descriptor version 1 (sm_100)
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
          ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 // kind::tf32, fp32 accumulate, A and B K-major, M = 128
-__host__ __device__ constexpr uint32_t make_idesc(int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// Bulk L2 prefetch of a contiguous global range (no registers, no smem): hides DRAM latency for the producers,
+// whose register prefetch (3 k-blocks = 48 KB per SM) alone cannot cover ~2 us of loaded-HBM latency.
+__device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
 }
 
 __device__ __forceinline__ float tf32_rna(float x) {
@@ -139,7 +170,32 @@ struct Smem {
   static constexpr int kTotal = kBBytes + kStages * kStageBytes + kBarBytes + 1024;  // + alignment slack
 };
 
-template <int N, int K>
+// Epilogue modes (compile-time, so that the fully unrolled TMEM->global loop stays small and branch-free;
+// the first version kept them as run-time flags and the 11 k-instruction kernel thrashed the I-cache):
+//   piecewise-linear activations are ONE code path  y = x > 0 ? x : slope*x   (none: slope 1, relu: slope 0)
+enum : int {
+  kModeStore = 0,        // D = acc
+  kModeAccumulate = 1,   // D += acc
+  kModeBiasPwl = 2,      // D = pwl(acc + bias)
+  kModeGradPwl = 3,      // D = acc * (aux > 0 ? 1 : slope)
+  kModeBiasSmooth = 4,   // D = tanh|sigmoid(acc + bias)
+  kModeGradSmooth = 5,   // D = acc * d tanh|sigmoid expressed through aux = activation output
+};
+
+template <int MODE>
+__device__ __forceinline__ float epilogue_op(float acc, float bias, float aux, float old, float slope, int act) {
+  if constexpr (MODE == kModeStore) return acc;
+  if constexpr (MODE == kModeAccumulate) return __fadd_rn(old, acc);
+  if constexpr (MODE == kModeBiasPwl) {
+    const float x = __fadd_rn(acc, bias);
+    return x > 0.0f ? x : __fmul_rn(x, slope);
+  }
+  if constexpr (MODE == kModeGradPwl) return __fmul_rn(acc, aux > 0.0f ? 1.0f : slope);
+  if constexpr (MODE == kModeBiasSmooth) return apply_act(__fadd_rn(acc, bias), act, slope);
+  return __fmul_rn(acc, act_grad_from_output(aux, act, slope));
+}
+
+template <int N, int K, int MODE>
 __global__ void __launch_bounds__(kThreadsGemm, 1) tf32x3_gemm_kernel(const GemmParams p) {
   using L = Smem<N, K>;
   constexpr int kKBlocks = L::kKBlocks;
@@ -158,20 +214,27 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) tf32x3_gemm_kernel(const Gemm
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int64_t num_tiles = (p.M + kTileM - 1) / kTileM;
+  // ablation switches for performance triage (scripts/gemm_ablate.py); all zero in production calls
+  const bool dbg_no_ldg = (p.epilogue >> 8) & 1, dbg_no_sts = (p.epilogue >> 9) & 1;
+  const bool dbg_no_mma = (p.epilogue >> 10) & 1, dbg_no_stg = (p.epilogue >> 11) & 1;
+  const bool dbg_no_fence = (p.epilogue >> 12) & 1, dbg_spin = (p.epilogue >> 13) & 1, dbg_no_tld = (p.epilogue >> 14) & 1;
+  long long* dbg_ts = ((p.epilogue >> 16) & 1) && blockIdx.x == 0 ? (long long*)p.aux : nullptr;  // [3][256][2]
+#define MBAR_WAIT(bar, par) do { if (dbg_spin) mbar_wait_spin(bar, par); else mbar_wait(bar, par); } while (0)
 
   // ---- one-time setup: barriers, TMEM, resident split weights ---------------------------------------------
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(bar_full + 8 * s, kProducerThreads);
+      mbar_init(bar_full + 8 * s, kProducerWarps);        // one arrival per producer warp
       mbar_init(bar_empty + 8 * s, 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_acc_full + 8 * a, 1);
-      mbar_init(bar_acc_empty + 8 * a, kEpilogueWarps * 32);
+      mbar_init(bar_acc_empty + 8 * a, kEpilogueWarps);   // one arrival per epilogue warp
     }
     fence_barrier_init();
   }
-  if (warp == kMmaWarp) tmem_alloc(tmem_slot, 2 * N);
+  constexpr int kTmemCols = 2 * ((N == 128) ? kTileM : N);
+  if (warp == kMmaWarp) tmem_alloc(tmem_slot, kTmemCols);
   for (int c = threadIdx.x; c < N * (K / 4); c += kThreadsGemm) {  // 16-byte chunks of Bt[N,K]
     const int n = c / (K / 4);
     const int k4 = c % (K / 4);
@@ -202,7 +265,7 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) tf32x3_gemm_kernel(const Gemm
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int64_t r = tile * kTileM + row0 + 32 * i;
-        if (r < p.M) {
+        if (r < p.M && !dbg_no_ldg) {
           const float* src = p.A + r * p.lda + kb * kKB + c16 * 4;
           float4 v;
           asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
@@ -223,11 +286,22 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) tf32x3_gemm_kernel(const Gemm
       }
     int stage = 0;
     uint32_t phase = 0;
+    constexpr int kL2Ahead = 3;  // tiles of this CTA kept on their way into L2
+    auto l2_prefetch_tile = [&](int64_t local_tile) {
+      const int64_t tile = (int64_t)blockIdx.x + local_tile * gridDim.x;
+      if (tile < num_tiles && pt < kTileM) {               // one 512-byte (K=128) row per thread
+        const int64_t r = tile * kTileM + pt;
+        if (r < p.M) prefetch_l2_bulk(p.A + r * p.lda, (uint32_t)(K * 4));
+      }
+    };
+    for (int t = 1; t <= kL2Ahead; ++t) l2_prefetch_tile(t);
     for (int64_t it0 = 0; it0 < total_kb; it0 += kPrefetch) {
 #pragma unroll
       for (int slot = 0; slot < kPrefetch; ++slot) {  // compile-time slot: the prefetch buffers stay in registers
         if (it0 + slot < total_kb) {
-          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          if ((it0 + slot) % kKBlocks == 0) l2_prefetch_tile((it0 + slot) / kKBlocks + kL2Ahead + 1);
+          MBAR_WAIT(bar_empty + 8 * stage, phase ^ 1);
+          if (dbg_ts && pt == 0 && it0 + slot < 256) dbg_ts[2 * (it0 + slot)] = clock64();
           const uint32_t hi = sA + stage * L::kStageBytes;
           const uint32_t lo = hi + L::kABlockBytes;
 #pragma unroll
@@ -238,10 +312,14 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) tf32x3_gemm_kernel(const Gemm
               v.x = __fmul_rn(s, v.x); v.y = __fmul_rn(s, v.y); v.z = __fmul_rn(s, v.z); v.w = __fmul_rn(s, v.w);
             }
             const uint32_t off = swz(row0 + 32 * i, c16);
-            split_store(hi + off, lo + off, v);
+            if (!dbg_no_sts) split_store(hi + off, lo + off, v);
           }
-          fence_proxy_async();
-          mbar_arrive(bar_full + 8 * stage);
+          // every writer fences its own generic-proxy stores towards the async proxy, the warp converges, and
+          // ONE lane arrives: 8 smem atomics per stage instead of 256 (the per-thread version cost 1.3 ms / 8 M rows)
+          if (!dbg_no_fence) fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_full + 8 * stage);
+          if (dbg_ts && pt == 0 && it0 + slot < 256) dbg_ts[2 * (it0 + slot) + 1] = clock64();
           if (it_load < total_kb) {
             load_block(it_load, buf[slot], scale_buf[slot]);
             ++it_load;
@@ -252,19 +330,33 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) tf32x3_gemm_kernel(const Gemm
     }
   } else if (warp == kMmaWarp) {
     // =========================== MMA ISSUER ===========================
-    constexpr uint32_t idesc = make_idesc(N);
+    // TRANSPOSED (N == 128): D^T[feature, edge] = W[feature, k] * X[edge, k]^T  (M = 128 features, N = 128 edges)
+    constexpr bool kT = (N == 128);
+    constexpr uint32_t idesc = kT ? make_idesc(128, kTileM) : make_idesc(kTileM, N);
+    constexpr int kAccCols = kT ? kTileM : N;
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    int dbg_it = 0;
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      mbar_wait(bar_acc_empty + 8 * acc, acc_phase ^ 1);
+      MBAR_WAIT(bar_acc_empty + 8 * acc, acc_phase ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccCols);
       for (int kb = 0; kb < kKBlocks; ++kb) {
-        mbar_wait(bar_full + 8 * stage, phase);
+        MBAR_WAIT(bar_full + 8 * stage, phase);
+        if (dbg_ts && lane == 0 && dbg_it < 256) dbg_ts[512 + 2 * dbg_it] = clock64();
         tc_fence_after();
-        if (lane == 0) {
+        if (lane == 0 && dbg_no_mma) {
+          if ((p.epilogue >> 15) & 1) {   // plain arrivals instead of tcgen05.commit (measures commit latency)
+            mbar_arrive(bar_empty + 8 * stage);
+            if (kb == kKBlocks - 1) mbar_arrive(bar_acc_full + 8 * acc);
+          } else {
+            umma_commit(bar_empty + 8 * stage);
+            if (kb == kKBlocks - 1) umma_commit(bar_acc_full + 8 * acc);
+          }
+        }
+        if (lane == 0 && !dbg_no_mma) {
           const uint32_t a_hi = sA + stage * L::kStageBytes;
           const uint32_t a_lo = a_hi + L::kABlockBytes;
           const uint32_t b_hi = sB + kb * L::kBBlockBytes;
@@ -276,63 +368,113 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) tf32x3_gemm_kernel(const Gemm
             const uint64_t dbh = make_smem_desc(b_hi + j * 32);
             const uint64_t dbl = make_smem_desc(b_lo + j * 32);
             // small terms first, the dominant hi*hi product last
-            umma_tf32(d_tmem, dal, dbh, idesc, (kb | j) != 0 ? 1u : 0u);
-            umma_tf32(d_tmem, dah, dbl, idesc, 1u);
-            umma_tf32(d_tmem, dah, dbh, idesc, 1u);
+            if constexpr (kT) {
+              umma_tf32(d_tmem, dbh, dal, idesc, (kb | j) != 0 ? 1u : 0u);
+              umma_tf32(d_tmem, dbl, dah, idesc, 1u);
+              umma_tf32(d_tmem, dbh, dah, idesc, 1u);
+            } else {
+              umma_tf32(d_tmem, dal, dbh, idesc, (kb | j) != 0 ? 1u : 0u);
+              umma_tf32(d_tmem, dah, dbl, idesc, 1u);
+              umma_tf32(d_tmem, dah, dbh, idesc, 1u);
+            }
           }
           umma_commit(bar_empty + 8 * stage);                 // smem stage free once these MMAs retire
           if (kb == kKBlocks - 1) umma_commit(bar_acc_full + 8 * acc);
         }
         __syncwarp();
+        if (dbg_ts && lane == 0 && dbg_it < 256) dbg_ts[512 + 2 * dbg_it + 1] = clock64();
+        ++dbg_it;
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     // =========================== EPILOGUE ===========================
+    constexpr bool kNeedAux = (MODE == kModeGradPwl || MODE == kModeGradSmooth);
+    constexpr bool kNeedBias = (MODE == kModeBiasPwl || MODE == kModeBiasSmooth);
     const int act = p.epilogue & 15;
-    const bool mul_grad = (p.epilogue & kEpiMulActGradFromOutput) != 0;
-    const bool accumulate = (p.epilogue & kEpiAccumulate) != 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    int dbg_tile = 0;
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      mbar_wait(bar_acc_full + 8 * acc, acc_phase);
+      MBAR_WAIT(bar_acc_full + 8 * acc, acc_phase);
+      if (dbg_ts && threadIdx.x == 0 && dbg_tile < 256) dbg_ts[1024 + 2 * dbg_tile] = clock64();
       tc_fence_after();
-      const int64_t r = tile * kTileM + warp * 32 + lane;     // TMEM lane == tile row
-      const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * N);
-#pragma unroll 1
-      for (int c0 = 0; c0 < N; c0 += 32) {
-        float v[32];
-        tmem_ld32(t_row + c0, v);
-        if (r < p.M) {
-          float* drow = p.D + r * p.ldd + c0;
+      if constexpr (N == 128) {
+        // TMEM lane == output feature; the 32 registers of one tcgen05.ld == 32 consecutive edges (tile rows):
+        // the 32 lanes of a warp store 32 consecutive floats of ONE output row -> a single 128-byte wavefront.
+        // Warp w owns TMEM lanes 32*(w%4).. (hardware rule) and the column half (w/4); the two 32-column loads of
+        // its half are issued back to back so the ~1k-cycle TMEM read latency is paid once per tile.
+        const int quad = warp & 3, half = warp >> 2;
+        const int f = quad * 32 + lane;
+        const float bias_f = (kNeedBias && p.bias != nullptr) ? __ldg(p.bias + f) : 0.0f;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kTileM + half * 64);
+        float v[2][32];
+        if (!dbg_no_tld) {
+          tmem_ld32_nowait(t_lane, v[0]);
+          tmem_ld32_nowait(t_lane + 32, v[1]);
+          tmem_ld_wait();
+        }
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-            if (p.bias != nullptr) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + 4 * q));
-              o.x = __fadd_rn(o.x, b.x); o.y = __fadd_rn(o.y, b.y); o.z = __fadd_rn(o.z, b.z); o.w = __fadd_rn(o.w, b.w);
+        for (int c = 0; c < 2; ++c) {
+          const int64_t r0 = tile * kTileM + half * 64 + c * 32;
+          float* dst = p.D + r0 * p.ldd + f;
+          const float* aux = kNeedAux ? p.aux + r0 * p.ld_aux + f : nullptr;
+          if (r0 + 32 <= p.M) {                                   // full chunk: no per-row predicate
+            if (!dbg_no_stg) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float y = kNeedAux ? *aux : 0.0f;
+                const float old = (MODE == kModeAccumulate) ? *dst : 0.0f;
+                *dst = epilogue_op<MODE>(v[c][j], bias_f, y, old, p.slope, act);
+                dst += p.ldd;
+                if (kNeedAux) aux += p.ld_aux;
+              }
             }
-            if (mul_grad) {
-              const float4 y = *reinterpret_cast<const float4*>(p.aux + r * p.ld_aux + c0 + 4 * q);
-              o.x = __fmul_rn(o.x, act_grad_from_output(y.x, act, p.slope));
-              o.y = __fmul_rn(o.y, act_grad_from_output(y.y, act, p.slope));
-              o.z = __fmul_rn(o.z, act_grad_from_output(y.z, act, p.slope));
-              o.w = __fmul_rn(o.w, act_grad_from_output(y.w, act, p.slope));
-            } else if (act != DMP_ACT_NONE) {
-              o.x = apply_act(o.x, act, p.slope); o.y = apply_act(o.y, act, p.slope);
-              o.z = apply_act(o.z, act, p.slope); o.w = apply_act(o.w, act, p.slope);
+          } else {
+            const int nvalid = (int)(p.M - r0);                   // may be <= 0
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (j < nvalid) {
+                const float y = kNeedAux ? aux[j * p.ld_aux] : 0.0f;
+                const float old = (MODE == kModeAccumulate) ? dst[j * p.ldd] : 0.0f;
+                dst[j * p.ldd] = epilogue_op<MODE>(v[c][j], bias_f, y, old, p.slope, act);
+              }
             }
-            if (accumulate) {
-              const float4 d = *reinterpret_cast<const float4*>(drow + 4 * q);
-              o.x = __fadd_rn(d.x, o.x); o.y = __fadd_rn(d.y, o.y); o.z = __fadd_rn(d.z, o.z); o.w = __fadd_rn(d.w, o.w);
+          }
+        }
+      } else {
+        // TMEM lane == tile row (N = 64 features: the M = 64 transposed form would leave half the lanes idle)
+        const int quad = warp & 3, half = warp >> 2;
+        const int64_t r = tile * kTileM + quad * 32 + lane;
+        const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * N);
+#pragma unroll 1
+        for (int c0 = half * (N / 2); c0 < (half + 1) * (N / 2); c0 += 32) {
+          float v[32];
+          tmem_ld32(t_row + c0, v);
+          if (r < p.M) {
+            float* drow = p.D + r * p.ldd + c0;
+            const float* arow = kNeedAux ? p.aux + r * p.ld_aux + c0 : nullptr;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              float4 b = make_float4(0.f, 0.f, 0.f, 0.f), y = b, d = b, o;
+              if (kNeedBias && p.bias != nullptr) b = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + 4 * q));
+              if (kNeedAux) y = *reinterpret_cast<const float4*>(arow + 4 * q);
+              if (MODE == kModeAccumulate) d = *reinterpret_cast<const float4*>(drow + 4 * q);
+              o.x = epilogue_op<MODE>(v[4 * q + 0], b.x, y.x, d.x, p.slope, act);
+              o.y = epilogue_op<MODE>(v[4 * q + 1], b.y, y.y, d.y, p.slope, act);
+              o.z = epilogue_op<MODE>(v[4 * q + 2], b.z, y.z, d.z, p.slope, act);
+              o.w = epilogue_op<MODE>(v[4 * q + 3], b.w, y.w, d.w, p.slope, act);
+              *reinterpret_cast<float4*>(drow + 4 * q) = o;
             }
-            *reinterpret_cast<float4*>(drow + 4 * q) = o;
           }
         }
       }
       tc_fence_before();
-      mbar_arrive(bar_acc_empty + 8 * acc);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acc_empty + 8 * acc);
+      if (dbg_ts && threadIdx.x == 0 && dbg_tile < 256) dbg_ts[1024 + 2 * dbg_tile + 1] = clock64();
+      ++dbg_tile;
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -340,15 +482,15 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) tf32x3_gemm_kernel(const Gemm
   // ---- teardown ---------------------------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
-  if (warp == kMmaWarp) tmem_dealloc(tmem_base, 2 * N);
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, kTmemCols);
 }
 
-template <int N, int K>
-static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
+template <int N, int K, int MODE>
+static int launch_gemm_mode(const GemmParams& p, cudaStream_t stream) {
   using L = Smem<N, K>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tf32x3_gemm_kernel<N, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    cudaError_t e = cudaFuncSetAttribute(tf32x3_gemm_kernel<N, K, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
     if (e != cudaSuccess) {
       set_error("gemm_tf32x3: cannot reserve %d bytes of shared memory: %s", L::kTotal, cudaGetErrorString(e));
       return DMP_ERR_CUDA;
@@ -357,8 +499,20 @@ static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
   }
   const int64_t tiles = (p.M + kTileM - 1) / kTileM;
   const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
-  tf32x3_gemm_kernel<N, K><<<grid, kThreadsGemm, L::kTotal, stream>>>(p);
+  tf32x3_gemm_kernel<N, K, MODE><<<grid, kThreadsGemm, L::kTotal, stream>>>(p);
   return launch_status("tf32x3_gemm_kernel");
+}
+
+template <int N, int K>
+static int launch_gemm(const GemmParams& p, int mode, cudaStream_t stream) {
+  switch (mode) {
+    case kModeStore: return launch_gemm_mode<N, K, kModeStore>(p, stream);
+    case kModeAccumulate: return launch_gemm_mode<N, K, kModeAccumulate>(p, stream);
+    case kModeBiasPwl: return launch_gemm_mode<N, K, kModeBiasPwl>(p, stream);
+    case kModeGradPwl: return launch_gemm_mode<N, K, kModeGradPwl>(p, stream);
+    case kModeBiasSmooth: return launch_gemm_mode<N, K, kModeBiasSmooth>(p, stream);
+    default: return launch_gemm_mode<N, K, kModeGradSmooth>(p, stream);
+  }
 }
 
 }  // namespace gemm
@@ -383,12 +537,26 @@ extern "C" int dmp_gemm_tf32x3(const float* A, int64_t lda, const float* row_sca
   DMP_CHECK_ARG(!(epilogue & kEpiMulActGradFromOutput) || (aux != nullptr && ld_aux >= N && ld_aux % 4 == 0),
                 "gemm_tf32x3: act' epilogue needs aux");
   DMP_CHECK_ARG(A != D, "gemm_tf32x3: D must not alias A");
+  const bool mul_grad = (epilogue & kEpiMulActGradFromOutput) != 0;
+  const bool accumulate = (epilogue & kEpiAccumulate) != 0;
+  DMP_CHECK_ARG(!(accumulate && (mul_grad || bias != nullptr || act != DMP_ACT_NONE)),
+                "gemm_tf32x3: accumulate cannot be combined with bias / activation epilogues");
+  DMP_CHECK_ARG(!(mul_grad && bias != nullptr), "gemm_tf32x3: act' epilogue takes no bias");
   GemmParams p;
   p.A = A; p.lda = lda; p.row_scale = row_scale; p.Bt = Bt; p.ldb = ldb; p.bias = bias;
   p.aux = aux; p.ld_aux = ld_aux; p.D = D; p.ldd = ldd; p.M = M; p.epilogue = epilogue; p.slope = slope;
+  const bool smooth = (act == DMP_ACT_TANH || act == DMP_ACT_SIGMOID);
+  if (act == DMP_ACT_NONE) p.slope = 1.0f;   // piecewise-linear family: none = slope 1, relu = slope 0
+  if (act == DMP_ACT_RELU) p.slope = 0.0f;
+  int mode;
+  if (accumulate) mode = kModeAccumulate;
+  else if (mul_grad) mode = smooth ? kModeGradSmooth : (act == DMP_ACT_NONE ? kModeStore : kModeGradPwl);
+  else if (smooth) mode = kModeBiasSmooth;
+  else if (bias != nullptr || act != DMP_ACT_NONE) mode = kModeBiasPwl;
+  else mode = kModeStore;
   cudaStream_t s = (cudaStream_t)stream;
-  if (N == 128 && K == 128) return launch_gemm<128, 128>(p, s);
-  if (N == 128 && K == 64) return launch_gemm<128, 64>(p, s);
-  if (N == 64 && K == 128) return launch_gemm<64, 128>(p, s);
-  return launch_gemm<64, 64>(p, s);
+  if (N == 128 && K == 128) return launch_gemm<128, 128>(p, mode, s);
+  if (N == 128 && K == 64) return launch_gemm<128, 64>(p, mode, s);
+  if (N == 64 && K == 128) return launch_gemm<64, 128>(p, mode, s);
+  return launch_gemm<64, 64>(p, mode, s);
 }
