@@ -225,3 +225,34 @@ def gemm_tf32x3(A, Wt, *, row_scale=None, bias=None, act="none", slope=0.0, aux=
               _lib.ptr(bias), _lib.ptr(aux if mul_act_grad else None), ld_aux, _lib.ptr(out), ldd, M, N, K, epi,
               float(slope), _stream(A), tag="gemm_tf32x3")
     return out
+
+
+_tn_ws = {}
+
+
+def gemm_tn_tf32x3(X, G, *, row_scale=None, out=None, accumulate=False):
+    """D (+)= (row_scale ⊙ X).T @ G on the tensor cores (3xTF32), X [E,M], G [E,N], M,N in {64,128}. Raw call."""
+    _lib.require_cuda(X, G, row_scale)
+    X, ldx = _lib.row_major(X)
+    G, ldg = _lib.row_major(G)
+    E, M = X.shape
+    N = G.shape[1]
+    if G.shape[0] != E:
+        raise ValueError("row counts differ: %s vs %s" % (tuple(X.shape), tuple(G.shape)))
+    if out is None:
+        if accumulate:
+            raise ValueError("accumulate=True needs `out`")
+        out = torch.empty((M, N), dtype=torch.float32, device=X.device)
+    _, ldd = _lib.row_major(out)
+    key = (str(X.device), M, N)
+    ws = _tn_ws.get(key)
+    if ws is None:
+        import ctypes
+        nb = ctypes.c_int64(0)
+        _lib.check(_lib.load().dmp_gemm_tn_workspace_bytes(M, N, ctypes.byref(nb)), "dmp_gemm_tn_workspace_bytes")
+        ws = _tn_ws[key] = torch.empty(nb.value, dtype=torch.uint8, device=X.device)
+    if row_scale is not None:
+        row_scale = row_scale.reshape(-1).contiguous()
+    _lib.call("dmp_gemm_tn_tf32x3", X.device, _lib.ptr(X), ldx, _lib.ptr(row_scale), _lib.ptr(G), ldg, _lib.ptr(out),
+              ldd, E, M, N, int(accumulate), _lib.ptr(ws), ws.numel(), _stream(X), tag="gemm_tn_tf32x3")
+    return out

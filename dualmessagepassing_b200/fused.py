@@ -16,7 +16,7 @@ Reference lines: SubgraphCountingMatching/models/dmpnn.py:111-156 (forward), SUR
 import torch
 
 from . import _lib
-from .functional import edge_backward, edge_update, gemm_tf32x3, segment_reduce
+from .functional import edge_backward, edge_update, gemm_tf32x3, gemm_tn_tf32x3, segment_reduce
 
 _ACT = {"none": _lib.ACT_NONE, "relu": _lib.ACT_RELU, "leaky_relu": _lib.ACT_LEAKY_RELU,
         "tanh": _lib.ACT_TANH, "sigmoid": _lib.ACT_SIGMOID}
@@ -82,6 +82,17 @@ def _rowmm(A, Wt, *, bias=None, act=_lib.ACT_NONE, slope=0.0, aux=None, mul_act_
     return r
 
 
+def _tnmm(X, G, *, row_scale=None):
+    """(row_scale ⊙ X).T @ G -- the K = rows long weight-gradient reduction; tensor cores when both widths allow."""
+    if (DENSE_BACKEND == "auto" and X.shape[0] > 0 and X.shape[1] in (64, 128) and G.shape[1] in (64, 128)
+            and X.stride(1) == 1 and G.stride(1) == 1 and X.stride(0) % 4 == 0 and G.stride(0) % 4 == 0
+            and X.data_ptr() % 16 == 0 and G.data_ptr() % 16 == 0):
+        return gemm_tn_tf32x3(X, G, row_scale=row_scale)
+    if row_scale is not None:
+        X = X * row_scale.reshape(-1, 1)
+    return X.t() @ G
+
+
 def _mlp_forward(pre, W1, b1, W2, b2, act, slope):
     """Linear -> act -> Linear (dmpnn.py:45-52 without BN). Returns (out, h1) with h1 = act(lin1)."""
     h1 = _rowmm(pre, W1, bias=b1, act=act, slope=slope)      # bias + activation in the GEMM epilogue
@@ -93,12 +104,12 @@ def _mlp_backward(g_out, pre, h1, W1, W2, act, slope, need_w):
     """Returns (g_pre written into h1's storage, dW1, db1, dW2, db2). Consumes h1."""
     dW2 = db2 = dW1 = db1 = None
     if need_w:
-        dW2 = g_out.t() @ h1
+        dW2 = _tnmm(g_out, h1)
         db2 = g_out.sum(0)
     # g1 = (g_out @ W2) * act'(h1): new edge-sized buffer, act' folded into the GEMM epilogue
     g1 = _rowmm(g_out, W2.t(), act=act, slope=slope, aux=h1, mul_act_grad=True)
     if need_w:
-        dW1 = g1.t() @ pre
+        dW1 = _tnmm(g1, pre)
         db1 = g1.sum(0)
     g_pre = _rowmm(g1, W1.t(), out=h1)   # h1 is dead: re-use its storage
     return g_pre, g1, dW1, db1, dW2, db2
@@ -248,23 +259,23 @@ class _FusedDMPLayer(torch.autograd.Function):
                 _rowmm(T[:, H:], out_w, out=dX_e, accumulate=True)
         d_in = d_out = d_src = d_dst = d_nloop = d_eloop = d_nb = d_eb = None
         if need_w:
-            d_nloop = X_v.t() @ gN
-            d_eloop = X_e.t() @ gE
-            d_sd = X_e.t() @ CG
-            d_dst = X_v_full.t() @ dQd
+            d_nloop = _tnmm(X_v, gN)
+            d_eloop = _tnmm(X_e, gE)
+            d_sd = _tnmm(X_e, CG)
+            d_dst = _tnmm(X_v_full, dQd)
             d_dst.sub_(d_sd)
-            d_src = X_v_full.t() @ dQs
+            d_src = _tnmm(X_v_full, dQs)
             d_src.add_(d_sd)
             if plan.rev_layout == "none":
-                d_in = X_e.t() @ T
+                d_in = _tnmm(X_e, T)
                 d_out = torch.zeros_like(out_w)
             elif plan.rev_layout == "halves":
                 h = E // 2
-                d_in = X_e[:h].t() @ T[:h]
-                d_out = X_e[h:].t() @ T[h:]
+                d_in = _tnmm(X_e[:h], T[:h])
+                d_out = _tnmm(X_e[h:], T[h:])
             else:
-                d_io = X_e.t() @ T
-                d_in, d_out = d_io[:, :H].contiguous(), d_io[:, H:].contiguous()
+                d_in = _tnmm(X_e, T[:, :H])
+                d_out = _tnmm(X_e, T[:, H:])
             if ctx.has_bias[0]:
                 d_nb = gN.sum(0)
             if ctx.has_bias[1]:

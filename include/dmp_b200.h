@@ -175,6 +175,20 @@ DMP_API int dmp_gemm_tf32x3(const float* A, int64_t lda, const float* row_scale,
                             const float* bias, const float* aux, int64_t ld_aux, float* D, int64_t ldd,
                             int64_t M, int64_t N, int64_t K, int epilogue, float slope, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Weight-gradient reduction on the tensor cores (3xTF32 split, fp32-level accuracy):
+ *
+ *   D[M,N] (+)= sum_e (row_scale[e] * X[e,0:M])^T * G[e,0:N]          M, N in {64,128}
+ *
+ * Replaces autograd's `X.t() @ G` for dW_eloop, dW_src/dst, dW_in/out and the MLP weight gradients
+ * (transposes of the matmuls at dmpnn.py:112-113,120-121,146-147,45-52).  Deterministic: every CTA owns
+ * a contiguous edge range, partials are added in CTA order.  workspace >= dmp_gemm_tn_workspace_bytes(M,N).
+ */
+DMP_API int dmp_gemm_tn_workspace_bytes(int64_t M, int64_t N, int64_t* bytes_host);
+DMP_API int dmp_gemm_tn_tf32x3(const float* X, int64_t ldx, const float* row_scale, const float* G, int64_t ldg,
+                               float* D, int64_t ldd, int64_t E, int64_t M, int64_t N, int accumulate,
+                               void* workspace, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,6 +13,12 @@ for (N, K) in [(128, 128), (64, 64)]:
         for _ in range(n): fn()
         e1.record(); torch.cuda.synchronize()
         return e0.elapsed_time(e1) / n
+    G = torch.randn(E, N, device="cuda")
+    ms_rc = t(lambda: A.t() @ G); ms_ro = t(lambda: F.gemm_tn_tf32x3(A, G))
+    refr = A.double().t() @ G.double()
+    er = lambda x: float((x.double() - refr).abs().max() / refr.abs().max())
+    print("   reduction X^T G: cuBLAS %.3f ms (err %.2g) | tf32x3 %.3f ms (%.0f GB/s, err %.2g)" % (
+        ms_rc, er(A.t() @ G), ms_ro, (E * K + E * N) * 4 / 1e6 / ms_ro, er(F.gemm_tn_tf32x3(A, G))))
     ms_c = t(lambda: torch.mm(A, Wt.t(), out=out))
     ms_o = t(lambda: F.gemm_tf32x3(A, Wt, out=out))
     gb = (E * K + E * N) * 4 / 1e9
