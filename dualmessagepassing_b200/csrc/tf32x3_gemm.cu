@@ -328,13 +328,21 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) tf32x3_gemm_kernel(const Gemm
           const float* aux = kNeedAux ? p.aux + r0 * p.ld_aux + f : nullptr;
           if (r0 + 32 <= p.M) {                                   // full chunk: no per-row predicate
             if (!dbg_no_stg) {
+              // operands of the epilogue (previous D for accumulate, activation output for act') are fetched as
+              // 32 independent loads BEFORE the first store: one latency per chunk instead of one per row
+              float t[32];
+              if constexpr (kNeedAux || MODE == kModeAccumulate) {
+                const float* src = kNeedAux ? aux : dst;
+                const int64_t lds = kNeedAux ? p.ld_aux : p.ldd;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) t[j] = src[j * lds];
+              }
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
-                const float y = kNeedAux ? *aux : 0.0f;
-                const float old = (MODE == kModeAccumulate) ? *dst : 0.0f;
+                const float y = kNeedAux ? t[j] : 0.0f;
+                const float old = (MODE == kModeAccumulate) ? t[j] : 0.0f;
                 *dst = epilogue_op<MODE>(v[c][j], bias_f, y, old, p.slope, act);
                 dst += p.ldd;
-                if (kNeedAux) aux += p.ld_aux;
               }
             }
           } else {
