@@ -28,7 +28,6 @@ namespace gemm {
 
 constexpr int kTileM = 128;
 constexpr int kKB = 32;                 // fp32 elements per k-block = one 128-byte swizzle row
-constexpr int kStages = 3;
 constexpr int kProducerWarps = 8;
 constexpr int kProducerThreads = kProducerWarps * 32;
 constexpr int kEpilogueWarps = 8;        // two warps per TMEM lane quadrant, each takes half of the columns
@@ -68,12 +67,16 @@ struct GemmParams {
 template <int N, int K>
 struct Smem {
   static constexpr int kKBlocks = K / kKB;
+  // N == 128 ("TS" form): the split weights live in TENSOR MEMORY as the MMA's A operand -- no smem copy, which
+  // halves the tensor core's smem read traffic and leaves room for 7 instead of 3 operand stages
+  static constexpr bool kTS = (N == 128);
+  static constexpr int kNumStages = kTS ? 7 : 3;
   static constexpr int kBBlockBytes = N * 128;                 // one k-block of B (hi or lo)
-  static constexpr int kBBytes = 2 * kKBlocks * kBBlockBytes;  // hi + lo
+  static constexpr int kBBytes = kTS ? 0 : 2 * kKBlocks * kBBlockBytes;  // hi + lo
   static constexpr int kABlockBytes = kTileM * 128;            // 16 KB
   static constexpr int kStageBytes = 2 * kABlockBytes;         // hi + lo
   static constexpr int kBarBytes = 256;
-  static constexpr int kTotal = kBBytes + kStages * kStageBytes + kBarBytes + 1024;  // + alignment slack
+  static constexpr int kTotal = kBBytes + kNumStages * kStageBytes + kBarBytes + 1024;  // + alignment slack
 };
 
 // Epilogue modes (compile-time, so that the fully unrolled TMEM->global loop stays small and branch-free;
@@ -105,6 +108,8 @@ template <int N, int K, int MODE>
 __global__ void __launch_bounds__(kThreadsGemm, 1) tf32x3_gemm_kernel(const GemmParams p) {
   using L = Smem<N, K>;
   constexpr int kKBlocks = L::kKBlocks;
+  constexpr int kStages = L::kNumStages;
+  constexpr bool kTS = L::kTS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sB = base;                                  // [hi kb0..][lo kb0..]
@@ -139,21 +144,49 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) tf32x3_gemm_kernel(const Gemm
     }
     fence_barrier_init();
   }
-  constexpr int kTmemCols = 2 * ((N == 128) ? kTileM : N);
+  // TMEM map (TS): [0,128) acc 0 | [128,256) acc 1 | [256,256+K) W_hi | [256+K,256+2K) W_lo   (lane = feature)
+  constexpr int kTmemCols = kTS ? 512 : 2 * N;
+  constexpr uint32_t kWhiCol = 256, kWloCol = 256 + K;
   if (warp == kMmaWarp) tmem_alloc(tmem_slot, kTmemCols);
-  for (int c = threadIdx.x; c < N * (K / 4); c += kThreadsGemm) {  // 16-byte chunks of Bt[N,K]
-    const int n = c / (K / 4);
-    const int k4 = c % (K / 4);
-    const float4 v = __ldg(reinterpret_cast<const float4*>(p.Bt + (int64_t)n * p.ldb + k4 * 4));
-    const int kb = k4 / 8, c16 = k4 % 8;
-    const uint32_t off = (uint32_t)kb * L::kBBlockBytes + swz(n, c16);
-    split_store(sB + off, sB + kKBlocks * L::kBBlockBytes + off, v);
+  if constexpr (!kTS) {
+    for (int c = threadIdx.x; c < N * (K / 4); c += kThreadsGemm) {  // 16-byte chunks of Bt[N,K]
+      const int n = c / (K / 4);
+      const int k4 = c % (K / 4);
+      const float4 v = __ldg(reinterpret_cast<const float4*>(p.Bt + (int64_t)n * p.ldb + k4 * 4));
+      const int kb = k4 / 8, c16 = k4 % 8;
+      const uint32_t off = (uint32_t)kb * L::kBBlockBytes + swz(n, c16);
+      split_store(sB + off, sB + kKBlocks * L::kBBlockBytes + off, v);
+    }
+    fence_proxy_async();
   }
-  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  if constexpr (kTS) {
+    if (warp < 4) {   // thread = weight row (output feature) = TMEM lane; 32 k-values per tcgen05.st
+      const int f = warp * 32 + lane;
+      const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < K; c0 += 32) {
+        float hi[32], lo[32];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(p.Bt + (int64_t)f * p.ldb + c0 + 4 * q));
+          hi[4 * q + 0] = tf32_rna(v.x); lo[4 * q + 0] = __fsub_rn(v.x, hi[4 * q + 0]);
+          hi[4 * q + 1] = tf32_rna(v.y); lo[4 * q + 1] = __fsub_rn(v.y, hi[4 * q + 1]);
+          hi[4 * q + 2] = tf32_rna(v.z); lo[4 * q + 2] = __fsub_rn(v.z, hi[4 * q + 2]);
+          hi[4 * q + 3] = tf32_rna(v.w); lo[4 * q + 3] = __fsub_rn(v.w, hi[4 * q + 3]);
+        }
+        tmem_st32(t_lane + kWhiCol + c0, hi);
+        tmem_st32(t_lane + kWloCol + c0, lo);
+      }
+      tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
 
   if (warp > kMmaWarp) {
     // =========================== PRODUCERS ===========================
@@ -194,10 +227,13 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) tf32x3_gemm_kernel(const Gemm
     uint32_t phase = 0;
     constexpr int kL2Ahead = 3;  // tiles of this CTA kept on their way into L2
     auto l2_prefetch_tile = [&](int64_t local_tile) {
+      // ONE thread, ONE bulk prefetch per tile (the tile's rows form one contiguous range of rows*lda floats).
+      // UBLKPF takes uniform operands: issued from many lanes the compiler serialises it lane by lane.
       const int64_t tile = (int64_t)blockIdx.x + local_tile * gridDim.x;
-      if (tile < num_tiles && pt < kTileM) {               // one 512-byte (K=128) row per thread
-        const int64_t r = tile * kTileM + pt;
-        if (r < p.M) prefetch_l2_bulk(p.A + r * p.lda, (uint32_t)(K * 4));
+      if (pt == 0 && tile < num_tiles) {
+        const int64_t r0 = tile * kTileM;
+        const int64_t rows = (p.M - r0) < kTileM ? (p.M - r0) : kTileM;
+        prefetch_l2_bulk(p.A + r0 * p.lda, (uint32_t)(((rows - 1) * p.lda + K) * 4));
       }
     };
     for (int t = 1; t <= kL2Ahead; ++t) l2_prefetch_tile(t);
@@ -271,14 +307,17 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) tf32x3_gemm_kernel(const Gemm
           for (int j = 0; j < kKB / 8; ++j) {
             const uint64_t dah = make_smem_desc(a_hi + j * 32);
             const uint64_t dal = make_smem_desc(a_lo + j * 32);
-            const uint64_t dbh = make_smem_desc(b_hi + j * 32);
-            const uint64_t dbl = make_smem_desc(b_lo + j * 32);
             // small terms first, the dominant hi*hi product last
             if constexpr (kT) {
-              umma_tf32(d_tmem, dbh, dal, idesc, (kb | j) != 0 ? 1u : 0u);
-              umma_tf32(d_tmem, dbl, dah, idesc, 1u);
-              umma_tf32(d_tmem, dbh, dah, idesc, 1u);
+              // weights = A operand read from TMEM (8 columns per k-step), edge tile = B operand from smem
+              const uint32_t w_hi = tmem_base + kWhiCol + (uint32_t)(kb * kKB + j * 8);
+              const uint32_t w_lo = tmem_base + kWloCol + (uint32_t)(kb * kKB + j * 8);
+              umma_tf32_ts(d_tmem, w_hi, dal, idesc, (kb | j) != 0 ? 1u : 0u);
+              umma_tf32_ts(d_tmem, w_lo, dah, idesc, 1u);
+              umma_tf32_ts(d_tmem, w_hi, dah, idesc, 1u);
             } else {
+              const uint64_t dbh = make_smem_desc(b_hi + j * 32);
+              const uint64_t dbl = make_smem_desc(b_lo + j * 32);
               umma_tf32(d_tmem, dal, dbh, idesc, (kb | j) != 0 ? 1u : 0u);
               umma_tf32(d_tmem, dah, dbl, idesc, 1u);
               umma_tf32(d_tmem, dah, dbh, idesc, 1u);

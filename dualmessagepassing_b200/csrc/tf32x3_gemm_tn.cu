@@ -153,13 +153,12 @@ __global__ void __launch_bounds__(kTnThreads, 1) tf32x3_gemm_tn_kernel(const TnP
       }
     };
     // contiguous edge range -> bulk L2 prefetch a few stages ahead (one 512-byte row per thread and operand)
-    auto l2_prefetch = [&](int64_t st) {
-      if (st < n_stages && pt < 2 * kTnEdges) {
-        const int64_t e = (s_begin + st) * kTnEdges + (pt & (kTnEdges - 1));
-        if (e < p.E) {
-          if (pt < kTnEdges) prefetch_l2_bulk(p.X + e * p.ldx, (uint32_t)(M * 4));
-          else prefetch_l2_bulk(p.G + e * p.ldg, (uint32_t)(N * 4));
-        }
+    auto l2_prefetch = [&](int64_t st) {   // one thread per operand, one bulk prefetch per 32-edge stage
+      if (st < n_stages && (pt == 0 || pt == 32)) {
+        const int64_t e0 = (s_begin + st) * kTnEdges;
+        const int64_t rows = (p.E - e0) < kTnEdges ? (p.E - e0) : kTnEdges;
+        if (pt == 0) prefetch_l2_bulk(p.X + e0 * p.ldx, (uint32_t)(((rows - 1) * p.ldx + M) * 4));
+        else prefetch_l2_bulk(p.G + e0 * p.ldg, (uint32_t)(((rows - 1) * p.ldg + N) * 4));
       }
     };
     constexpr int kL2Ahead = 12;
