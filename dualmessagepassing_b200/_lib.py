@@ -39,7 +39,7 @@ SIGNATURES = {
     "dmp_gate_residual": [_vp, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i32, _f32, _vp],
     "dmp_gate_residual_backward": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _i32, _f32, _vp],
     "dmp_gemm_tn_workspace_bytes": [_i64, _i64, ctypes.POINTER(ctypes.c_int64)],
-    "dmp_gemm_tn_tf32x3": [_vp, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _i32, _vp, _i64, _vp],
+    "dmp_gemm_tn_tf32x3": [_vp, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _i32, _vp, _i64, _vp],
     "dmp_gemm_tf32x3": [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _i32, _f32, _vp],
 }
 

@@ -36,6 +36,8 @@ struct TnParams {
   const float* row_scale;
   const float* G; int64_t ldg;
   float* partial;        // [grid][N][M]  (transposed: lanes = m are contiguous)
+  float* part_sx;        // [grid][M] column sums of X (unscaled) or NULL
+  float* part_sg;        // [grid][N] column sums of G or NULL
   int64_t E;
   uint32_t lbo, sbo, kadv;   // descriptor geometry (bytes); defaults set by the host wrapper
   uint32_t idesc_xor, ltype;
@@ -53,7 +55,8 @@ struct TnSmem {
                                                             // with M = 128 (for M = 64 the upper two blocks stay zero)
   static constexpr int kGBytes = kTnEdges * N * 4;
   static constexpr int kStageBytes = 2 * kXBytes + 2 * kGBytes;
-  static constexpr int kTotal = kTnStages * kStageBytes + 256 + 1024;
+  static constexpr int kSumBytes = 2 * kTnProducerWarps * 128 * 4;   // per-warp column-sum scratch (X and G)
+  static constexpr int kTotal = kTnStages * kStageBytes + 256 + kSumBytes + 1024;
 };
 
 // smem offset of 16-byte chunk c16 (4 features) of edge row k inside a [32 edges x F features] MN-major tile.
@@ -80,6 +83,7 @@ __global__ void __launch_bounds__(kTnThreads, 1) tf32x3_gemm_tn_kernel(const TnP
   const uint32_t bar_acc_full = sBar + 16 * kTnStages, bar_acc_empty = bar_acc_full + 16;
   const uint32_t tmem_slot = bar_acc_empty + 16;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  float* sum_scratch = reinterpret_cast<float*>(smem_raw + (sBar + 256 - smem_u32(smem_raw)));   // [2][8 warps][128]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // this CTA's contiguous range of 32-edge stages
@@ -123,6 +127,9 @@ __global__ void __launch_bounds__(kTnThreads, 1) tf32x3_gemm_tn_kernel(const TnP
     constexpr int kXPer = kXChunks / kTnProducerThreads, kGPer = kGChunks / kTnProducerThreads;   // 4 (or 2)
     float4 bx[kTnPrefetch][kXPer], bg[kTnPrefetch][kGPer];
     float sc[kTnPrefetch][kXPer];
+    // bias gradients for free: a thread always handles the same 4 columns (256 % (M/4) == 0), so it keeps running
+    // column sums of everything it streams; rows past E are zero-filled and add nothing
+    float4 sum_x = make_float4(0.f, 0.f, 0.f, 0.f), sum_g = sum_x;
     auto load_stage = [&](int64_t st, float4 (&dx)[kXPer], float4 (&dg)[kGPer], float (&s)[kXPer]) {
       const int64_t e0 = (s_begin + st) * kTnEdges;
 #pragma unroll
@@ -184,6 +191,8 @@ __global__ void __launch_bounds__(kTnThreads, 1) tf32x3_gemm_tn_kernel(const TnP
           for (int i = 0; i < kXPer; ++i) {
             const int c = pt + kTnProducerThreads * i;
             float4 v = bx[slot][i];
+            sum_x.x = __fadd_rn(sum_x.x, v.x); sum_x.y = __fadd_rn(sum_x.y, v.y);
+            sum_x.z = __fadd_rn(sum_x.z, v.z); sum_x.w = __fadd_rn(sum_x.w, v.w);
             if (p.row_scale != nullptr) {
               const float s = sc[slot][i];
               v.x = __fmul_rn(s, v.x); v.y = __fmul_rn(s, v.y); v.z = __fmul_rn(s, v.z); v.w = __fmul_rn(s, v.w);
@@ -195,7 +204,10 @@ __global__ void __launch_bounds__(kTnThreads, 1) tf32x3_gemm_tn_kernel(const TnP
           for (int i = 0; i < kGPer; ++i) {
             const int c = pt + kTnProducerThreads * i;
             const uint32_t off = swz_mn(c / (N / 4), c % (N / 4));
-            split_store(g_hi + off, g_lo + off, bg[slot][i]);
+            const float4 gv = bg[slot][i];
+            sum_g.x = __fadd_rn(sum_g.x, gv.x); sum_g.y = __fadd_rn(sum_g.y, gv.y);
+            sum_g.z = __fadd_rn(sum_g.z, gv.z); sum_g.w = __fadd_rn(sum_g.w, gv.w);
+            split_store(g_hi + off, g_lo + off, gv);
           }
           fence_proxy_async();
           __syncwarp();
@@ -206,6 +218,34 @@ __global__ void __launch_bounds__(kTnThreads, 1) tf32x3_gemm_tn_kernel(const TnP
           }
           if (++stage == kTnStages) { stage = 0; phase ^= 1; }
         }
+      }
+    }
+    if (p.part_sx != nullptr || p.part_sg != nullptr) {
+      // threads with equal (pt % chunks-per-row) own the same columns: with 32 chunks per row that is one lane of each
+      // of the 8 warps; with 16 chunks per row (64 features) lanes l and l+16 of every warp as well
+      const int pw = pt >> 5;
+      float* sx = sum_scratch + pw * 128;
+      float* sg = sum_scratch + (kTnProducerWarps + pw) * 128;
+      if (M == 64) {
+        sum_x.x += __shfl_down_sync(0xffffffffu, sum_x.x, 16); sum_x.y += __shfl_down_sync(0xffffffffu, sum_x.y, 16);
+        sum_x.z += __shfl_down_sync(0xffffffffu, sum_x.z, 16); sum_x.w += __shfl_down_sync(0xffffffffu, sum_x.w, 16);
+      }
+      if (N == 64) {
+        sum_g.x += __shfl_down_sync(0xffffffffu, sum_g.x, 16); sum_g.y += __shfl_down_sync(0xffffffffu, sum_g.y, 16);
+        sum_g.z += __shfl_down_sync(0xffffffffu, sum_g.z, 16); sum_g.w += __shfl_down_sync(0xffffffffu, sum_g.w, 16);
+      }
+      if (lane < M / 4) *reinterpret_cast<float4*>(sx + 4 * lane) = sum_x;
+      if (lane < N / 4) *reinterpret_cast<float4*>(sg + 4 * lane) = sum_g;
+      asm volatile("bar.sync 1, %0;" ::"n"(kTnProducerThreads) : "memory");
+      if (pt < M && p.part_sx != nullptr) {
+        float t = 0.0f;
+        for (int w = 0; w < kTnProducerWarps; ++w) t = __fadd_rn(t, sum_scratch[w * 128 + pt]);
+        p.part_sx[(int64_t)blockIdx.x * M + pt] = t;
+      }
+      if (pt < N && p.part_sg != nullptr) {
+        float t = 0.0f;
+        for (int w = 0; w < kTnProducerWarps; ++w) t = __fadd_rn(t, sum_scratch[(kTnProducerWarps + w) * 128 + pt]);
+        p.part_sg[(int64_t)blockIdx.x * N + pt] = t;
       }
     }
   } else if (warp == kTnMmaWarp) {
@@ -291,9 +331,23 @@ __global__ void __launch_bounds__(kTnThreads, 1) tf32x3_gemm_tn_kernel(const TnP
 
 // D[m, n] (+)= sum over CTAs (ascending) of partial[cta][n][m]
 __global__ void __launch_bounds__(256) tn_reduce_kernel(const float* __restrict__ partial, int parts, int M, int N,
-                                                        float* __restrict__ D, int64_t ldd, int accumulate) {
+                                                        float* __restrict__ D, int64_t ldd, int accumulate,
+                                                        const float* __restrict__ part_sx, float* __restrict__ sum_x,
+                                                        const float* __restrict__ part_sg, float* __restrict__ sum_g) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // over N*M, m fastest (coalesced partial reads)
-  if (idx >= M * N) return;
+  if (idx >= M * N) {
+    const int j = idx - M * N;                               // tail threads: the column sums
+    if (j < M && sum_x != nullptr) {
+      float s = 0.0f;
+      for (int c = 0; c < parts; ++c) s = __fadd_rn(s, part_sx[(int64_t)c * M + j]);
+      sum_x[j] = s;
+    } else if (j >= M && j < M + N && sum_g != nullptr) {
+      float s = 0.0f;
+      for (int c = 0; c < parts; ++c) s = __fadd_rn(s, part_sg[(int64_t)c * N + (j - M)]);
+      sum_g[j - M] = s;
+    }
+    return;
+  }
   const int n = idx / M, m = idx % M;
   float s = 0.0f;
   for (int c = 0; c < parts; ++c) s = __fadd_rn(s, partial[(int64_t)c * M * N + idx]);
@@ -323,13 +377,13 @@ static int launch_tn(const TnParams& p, unsigned grid, cudaStream_t stream) {
 extern "C" int dmp_gemm_tn_workspace_bytes(int64_t M, int64_t N, int64_t* bytes_host) {
   using namespace dmp;
   DMP_CHECK_ARG(bytes_host != nullptr, "gemm_tn_workspace_bytes: null output");
-  *bytes_host = (int64_t)kNumSMs * M * N * 4;
+  *bytes_host = (int64_t)kNumSMs * (M * N + M + N) * 4;
   return DMP_OK;
 }
 
 extern "C" int dmp_gemm_tn_tf32x3(const float* X, int64_t ldx, const float* row_scale, const float* G, int64_t ldg,
-                                  float* D, int64_t ldd, int64_t E, int64_t M, int64_t N, int accumulate,
-                                  void* workspace, int64_t workspace_bytes, void* stream) {
+                                  float* D, int64_t ldd, float* colsum_x, float* colsum_g, int64_t E, int64_t M,
+                                  int64_t N, int accumulate, void* workspace, int64_t workspace_bytes, void* stream) {
   using namespace dmp;
   using namespace dmp::gemm;
   DMP_CHECK_ARG(E >= 0, "gemm_tn_tf32x3: negative E");
@@ -341,10 +395,13 @@ extern "C" int dmp_gemm_tn_tf32x3(const float* X, int64_t ldx, const float* row_
   const int64_t stages = (E + kTnEdges - 1) / kTnEdges;
   int64_t grid = stages < kNumSMs ? stages : kNumSMs;
   if (grid < 1) grid = 1;
-  DMP_CHECK_ARG(workspace != nullptr && workspace_bytes >= grid * M * N * 4, "gemm_tn_tf32x3: workspace too small");
+  DMP_CHECK_ARG(workspace != nullptr && workspace_bytes >= grid * (M * N + M + N) * 4,
+                "gemm_tn_tf32x3: workspace too small");
   TnParams p;
   p.X = X; p.ldx = ldx; p.row_scale = row_scale; p.G = G; p.ldg = ldg;
   p.partial = static_cast<float*>(workspace); p.E = E;
+  p.part_sx = colsum_x ? p.partial + grid * M * N : nullptr;
+  p.part_sg = colsum_g ? p.partial + grid * (M * N + M) : nullptr;
   // 4096 B between 32-feature blocks (LBO), 512 B between 4-edge atoms (SBO), 1024 B per MMA k-step (8 edges)
   p.lbo = kTnEdges * 128; p.sbo = 512; p.kadv = 1024; p.idesc_xor = 0; p.ltype = 1;
   if (const char* dbg = getenv("DMP_TN_DBG"))
@@ -356,7 +413,8 @@ extern "C" int dmp_gemm_tn_tf32x3(const float* X, int64_t ldx, const float* row_
   else if (M == 64 && N == 128) rc = launch_tn<64, 128>(p, (unsigned)grid, s);
   else rc = launch_tn<64, 64>(p, (unsigned)grid, s);
   if (rc != DMP_OK) return rc;
-  const int total = (int)(M * N);
-  tn_reduce_kernel<<<(total + 255) / 256, 256, 0, s>>>(p.partial, (int)grid, (int)M, (int)N, D, ldd, accumulate);
+  const int total = (int)(M * N + M + N);
+  tn_reduce_kernel<<<(total + 255) / 256, 256, 0, s>>>(p.partial, (int)grid, (int)M, (int)N, D, ldd, accumulate,
+                                                      p.part_sx, colsum_x, p.part_sg, colsum_g);
   return launch_status("tn_reduce_kernel");
 }

@@ -230,8 +230,9 @@ def gemm_tf32x3(A, Wt, *, row_scale=None, bias=None, act="none", slope=0.0, aux=
 _tn_ws = {}
 
 
-def gemm_tn_tf32x3(X, G, *, row_scale=None, out=None, accumulate=False):
-    """D (+)= (row_scale ⊙ X).T @ G on the tensor cores (3xTF32), X [E,M], G [E,N], M,N in {64,128}. Raw call."""
+def gemm_tn_tf32x3(X, G, *, row_scale=None, out=None, accumulate=False, colsum_x=False, colsum_g=False):
+    """D (+)= (row_scale ⊙ X).T @ G on the tensor cores (3xTF32), X [E,M], G [E,N], M,N in {64,128}. Raw call.
+    With colsum_x / colsum_g also returns X.sum(0) (unscaled) / G.sum(0): (D, sum_x or None, sum_g or None)."""
     _lib.require_cuda(X, G, row_scale)
     X, ldx = _lib.row_major(X)
     G, ldg = _lib.row_major(G)
@@ -253,6 +254,11 @@ def gemm_tn_tf32x3(X, G, *, row_scale=None, out=None, accumulate=False):
         ws = _tn_ws[key] = torch.empty(nb.value, dtype=torch.uint8, device=X.device)
     if row_scale is not None:
         row_scale = row_scale.reshape(-1).contiguous()
+    sx = torch.empty(M, dtype=torch.float32, device=X.device) if colsum_x else None
+    sg = torch.empty(N, dtype=torch.float32, device=X.device) if colsum_g else None
     _lib.call("dmp_gemm_tn_tf32x3", X.device, _lib.ptr(X), ldx, _lib.ptr(row_scale), _lib.ptr(G), ldg, _lib.ptr(out),
-              ldd, E, M, N, int(accumulate), _lib.ptr(ws), ws.numel(), _stream(X), tag="gemm_tn_tf32x3")
+              ldd, _lib.ptr(sx), _lib.ptr(sg), E, M, N, int(accumulate), _lib.ptr(ws), ws.numel(), _stream(X),
+              tag="gemm_tn_tf32x3")
+    if colsum_x or colsum_g:
+        return out, sx, sg
     return out

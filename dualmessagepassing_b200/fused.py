@@ -61,11 +61,13 @@ def _use_tc(A, Wt):
 
 
 def _rowmm(A, Wt, *, bias=None, act=_lib.ACT_NONE, slope=0.0, aux=None, mul_act_grad=False, accumulate=False,
-           out=None):
+           out=None, row_scale=None):
     """out (+)= epilogue(A @ Wt.T); Wt is [N,K] (nn.Linear layout).  One launch on the tensor-core path."""
     if _use_tc(A, Wt) and (out is None or (out.stride(1) == 1 and out.stride(0) % 4 == 0 and out.data_ptr() % 16 == 0)):
         return gemm_tf32x3(A, Wt.contiguous(), bias=bias, act=_ACT_NAME[act], slope=slope, aux=aux,
-                           mul_act_grad=mul_act_grad, accumulate=accumulate, out=out)
+                           mul_act_grad=mul_act_grad, accumulate=accumulate, out=out, row_scale=row_scale)
+    if row_scale is not None:
+        A = A * row_scale.reshape(-1, 1)
     if accumulate:
         out.addmm_(A, Wt.t())
         return out
@@ -82,15 +84,19 @@ def _rowmm(A, Wt, *, bias=None, act=_lib.ACT_NONE, slope=0.0, aux=None, mul_act_
     return r
 
 
-def _tnmm(X, G, *, row_scale=None):
-    """(row_scale ⊙ X).T @ G -- the K = rows long weight-gradient reduction; tensor cores when both widths allow."""
+def _tnmm(X, G, *, row_scale=None, colsum_x=False, colsum_g=False):
+    """(row_scale ⊙ X).T @ G -- the K = rows long weight-gradient reduction; tensor cores when both widths allow.
+    colsum_x / colsum_g: also return X.sum(0) / G.sum(0) (bias gradients) -> (D, sum_x, sum_g)."""
+    want_sums = colsum_x or colsum_g
     if (DENSE_BACKEND == "auto" and X.shape[0] > 0 and X.shape[1] in (64, 128) and G.shape[1] in (64, 128)
             and X.stride(1) == 1 and G.stride(1) == 1 and X.stride(0) % 4 == 0 and G.stride(0) % 4 == 0
             and X.data_ptr() % 16 == 0 and G.data_ptr() % 16 == 0):
-        return gemm_tn_tf32x3(X, G, row_scale=row_scale)
-    if row_scale is not None:
-        X = X * row_scale.reshape(-1, 1)
-    return X.t() @ G
+        return gemm_tn_tf32x3(X, G, row_scale=row_scale, colsum_x=colsum_x, colsum_g=colsum_g)
+    Xs = X * row_scale.reshape(-1, 1) if row_scale is not None else X
+    D = Xs.t() @ G
+    if want_sums:
+        return D, (X.sum(0) if colsum_x else None), (G.sum(0) if colsum_g else None)
+    return D
 
 
 def _mlp_forward(pre, W1, b1, W2, b2, act, slope):
@@ -104,13 +110,11 @@ def _mlp_backward(g_out, pre, h1, W1, W2, act, slope, need_w):
     """Returns (g_pre written into h1's storage, dW1, db1, dW2, db2). Consumes h1."""
     dW2 = db2 = dW1 = db1 = None
     if need_w:
-        dW2 = _tnmm(g_out, h1)
-        db2 = g_out.sum(0)
+        dW2, db2, _ = _tnmm(g_out, h1, colsum_x=True)
     # g1 = (g_out @ W2) * act'(h1): new edge-sized buffer, act' folded into the GEMM epilogue
     g1 = _rowmm(g_out, W2.t(), act=act, slope=slope, aux=h1, mul_act_grad=True)
     if need_w:
-        dW1 = _tnmm(g1, pre)
-        db1 = g1.sum(0)
+        dW1, db1, _ = _tnmm(g1, pre, colsum_x=True)
     g_pre = _rowmm(g1, W1.t(), out=h1)   # h1 is dead: re-use its storage
     return g_pre, g1, dW1, db1, dW2, db2
 
@@ -226,8 +230,10 @@ class _FusedDMPLayer(torch.autograd.Function):
         else:
             T = torch.zeros((E, m_cols), dtype=gE.dtype, device=gE.device) if ctx.m_off else \
                 torch.empty((E, H), dtype=gE.dtype, device=gE.device)
-        CG = buf2 if buf2 is not None else torch.empty((E, H), dtype=gE.dtype, device=gE.device)
-        edge_backward(plan, ctx.norm_flat, gN_full, gE, t_rev_col_offset=ctx.m_off, T=T, CG=CG)
+        # d(coef * P) = coef ⊙ gE is never materialised: both of its consumers (dX_e and dW_sd) take `coef` as a
+        # per-row scale of their streamed operand (fp32 product rounded exactly like the reference's `coef * gE`)
+        edge_backward(plan, ctx.norm_flat, gN_full, gE, want_CG=False, t_rev_col_offset=ctx.m_off, T=T)
+        del buf2
         del gN_full
 
         # ---- dense backward --------------------------------------------------------------------------------
@@ -247,7 +253,7 @@ class _FusedDMPLayer(torch.autograd.Function):
                 del partial
         if need_xe:
             dX_e = _rowmm(gE, eloop_w)
-            _rowmm(CG, w_sd, out=dX_e, accumulate=True)
+            _rowmm(gE, w_sd, out=dX_e, accumulate=True, row_scale=plan.coef)
             if plan.rev_layout == "none":
                 _rowmm(T, in_w, out=dX_e, accumulate=True)
             elif plan.rev_layout == "halves":
@@ -259,9 +265,13 @@ class _FusedDMPLayer(torch.autograd.Function):
                 _rowmm(T[:, H:], out_w, out=dX_e, accumulate=True)
         d_in = d_out = d_src = d_dst = d_nloop = d_eloop = d_nb = d_eb = None
         if need_w:
-            d_nloop = _tnmm(X_v, gN)
-            d_eloop = _tnmm(X_e, gE)
-            d_sd = _tnmm(X_e, CG)
+            d_nloop, _, d_nb = _tnmm(X_v, gN, colsum_g=True)
+            d_eloop, _, d_eb = _tnmm(X_e, gE, colsum_g=True)
+            if not ctx.has_bias[0]:
+                d_nb = None
+            if not ctx.has_bias[1]:
+                d_eb = None
+            d_sd = _tnmm(gE, X_e, row_scale=plan.coef).t()   # ((coef ⊙ gE)^T X_e)^T: the scale rides on gE, as in autograd
             d_dst = _tnmm(X_v_full, dQd)
             d_dst.sub_(d_sd)
             d_src = _tnmm(X_v_full, dQs)
@@ -276,10 +286,6 @@ class _FusedDMPLayer(torch.autograd.Function):
             else:
                 d_in = _tnmm(X_e, T[:, :H])
                 d_out = _tnmm(X_e, T[:, H:])
-            if ctx.has_bias[0]:
-                d_nb = gN.sum(0)
-            if ctx.has_bias[1]:
-                d_eb = gE.sum(0)
         mb = ctx.mlp_bias
         if part is not None and need_w:
             # every weight gradient above is a partial sum over this rank's nodes/edges

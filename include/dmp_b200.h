@@ -183,11 +183,13 @@ DMP_API int dmp_gemm_tf32x3(const float* A, int64_t lda, const float* row_scale,
  * Replaces autograd's `X.t() @ G` for dW_eloop, dW_src/dst, dW_in/out and the MLP weight gradients
  * (transposes of the matmuls at dmpnn.py:112-113,120-121,146-147,45-52).  Deterministic: every CTA owns
  * a contiguous edge range, partials are added in CTA order.  workspace >= dmp_gemm_tn_workspace_bytes(M,N).
+ * colsum_x [M] / colsum_g [N] (either may be NULL) additionally receive sum_e X[e,:] (unscaled) / sum_e G[e,:]
+ * -- the bias gradients (dnbias, debias, MLP db) come for free from the rows the kernel streams anyway.
  */
 DMP_API int dmp_gemm_tn_workspace_bytes(int64_t M, int64_t N, int64_t* bytes_host);
 DMP_API int dmp_gemm_tn_tf32x3(const float* X, int64_t ldx, const float* row_scale, const float* G, int64_t ldg,
-                               float* D, int64_t ldd, int64_t E, int64_t M, int64_t N, int accumulate,
-                               void* workspace, int64_t workspace_bytes, void* stream);
+                               float* D, int64_t ldd, float* colsum_x, float* colsum_g, int64_t E, int64_t M,
+                               int64_t N, int accumulate, void* workspace, int64_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -117,3 +117,19 @@ def test_gemm_tn_row_scale_accumulate_strided():
     F.gemm_tn_tf32x3(X, G, row_scale=c, out=D, accumulate=True)
     ref = D0.double() + (c.double().unsqueeze(1) * X.double()).t() @ G.double()
     assert float((D.double() - ref).abs().max() / ref.abs().max()) <= 1e-5
+
+
+@pytest.mark.parametrize("M,N", [(128, 128), (64, 64), (128, 64)])
+def test_gemm_tn_column_sums(M, N):
+    """Bias gradients ride along: column sums of both streamed operands (unscaled X, G)."""
+    from dualmessagepassing_b200 import functional as F
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    E = 123457
+    X = torch.randn(E, M, device="cuda", generator=g) + 0.5
+    G = torch.randn(E, N, device="cuda", generator=g) - 0.25
+    c = torch.rand(E, device="cuda", generator=g)
+    D, sx, sg = F.gemm_tn_tf32x3(X, G, row_scale=c, colsum_x=True, colsum_g=True)
+    torch.testing.assert_close(sx.double(), X.double().sum(0), rtol=1e-6, atol=1e-6 * float(X.double().sum(0).abs().max()))
+    torch.testing.assert_close(sg.double(), G.double().sum(0), rtol=1e-6, atol=1e-6 * float(G.double().sum(0).abs().max()))
+    ref = (c.double().unsqueeze(1) * X.double()).t() @ G.double()
+    assert float((D.double() - ref).abs().max() / ref.abs().max()) <= 1e-5
