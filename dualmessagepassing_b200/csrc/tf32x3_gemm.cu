@@ -195,78 +195,152 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) tf32x3_gemm_kernel(const Gemm
     const int c16 = pt & 7;
     const int row0 = pt >> 3;                                   // rows row0 + 32*i
     const int64_t total_kb = ((num_tiles - (int64_t)blockIdx.x + gridDim.x - 1) / gridDim.x) * kKBlocks;
-    float4 buf[kPrefetch][4];
-    float scale_buf[kPrefetch][4];
-    int64_t it_load = 0;
-    auto load_block = [&](int64_t it, float4 (&dst)[4], float (&sc)[4]) {
-      const int64_t tile = (int64_t)blockIdx.x + (it / kKBlocks) * gridDim.x;
-      const int kb = (int)(it % kKBlocks);
+    if constexpr (kTS) {
+      // ---- cp.async producer (N == 128): raw fp32 rows go global -> smem asynchronously (kCopyDepth k-blocks =
+      // 80 KB per SM in flight, no register staging); the raw tile IS the hi operand (a kind::tf32 MMA ignores the low
+      // 13 mantissa bits), the producer only adds lo = x - trunc_tf32(x).  ~2x fewer instructions per stage than the
+      // register path, which was issue/latency bound (ncu: producers 58 % busy, 14 % waiting on loads).
+      constexpr int kCopyDepth = kStages - 2;
+      uint32_t offs[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int64_t r = tile * kTileM + row0 + 32 * i;
-        if (r < p.M && !dbg_no_ldg) {
-          const float* src = p.A + r * p.lda + kb * kKB + c16 * 4;
-          float4 v;
-          asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                       : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(src));
-          dst[i] = v;
-          sc[i] = p.row_scale != nullptr ? __ldg(p.row_scale + r) : 1.0f;
-        } else {
-          dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          sc[i] = 1.0f;
+      for (int i = 0; i < 4; ++i) offs[i] = swz(row0 + 32 * i, c16);
+      int istage = 0;
+      uint32_t iphase = 0;
+      auto issue = [&](int64_t it) {
+        MBAR_WAIT(bar_empty + 8 * istage, iphase ^ 1);
+        const int64_t tile = (int64_t)blockIdx.x + (it / kKBlocks) * gridDim.x;
+        const int kb = (int)(it % kKBlocks);
+        const uint32_t hi = sA + istage * L::kStageBytes;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int64_t r = tile * kTileM + row0 + 32 * i;
+          const bool ok = r < p.M;
+          cp_async16(hi + offs[i], ok ? (const void*)(p.A + r * p.lda + kb * kKB + c16 * 4) : (const void*)p.A, ok ? 16u : 0u);
         }
-      }
-    };
+        if (++istage == kStages) { istage = 0; iphase ^= 1; }
+      };
+      auto l2_prefetch_tile = [&](int64_t local_tile) {
+        const int64_t tile = (int64_t)blockIdx.x + local_tile * gridDim.x;
+        if (pt == 0 && tile < num_tiles) {
+          const int64_t r0 = tile * kTileM;
+          const int64_t rows = (p.M - r0) < kTileM ? (p.M - r0) : kTileM;
+          prefetch_l2_bulk(p.A + r0 * p.lda, (uint32_t)(((rows - 1) * p.lda + K) * 4));
+        }
+      };
+      constexpr int kL2Ahead = 4;
+      for (int t = 2; t <= kL2Ahead; ++t) l2_prefetch_tile(t);
 #pragma unroll
-    for (int slot = 0; slot < kPrefetch; ++slot)
-      if (slot < total_kb) {
-        load_block(slot, buf[slot], scale_buf[slot]);
-        ++it_load;
+      for (int d = 0; d < kCopyDepth; ++d) {
+        if (d < total_kb) issue(d);
+        cp_async_commit();
       }
-    int stage = 0;
-    uint32_t phase = 0;
-    constexpr int kL2Ahead = 3;  // tiles of this CTA kept on their way into L2
-    auto l2_prefetch_tile = [&](int64_t local_tile) {
-      // ONE thread, ONE bulk prefetch per tile (the tile's rows form one contiguous range of rows*lda floats).
-      // UBLKPF takes uniform operands: issued from many lanes the compiler serialises it lane by lane.
-      const int64_t tile = (int64_t)blockIdx.x + local_tile * gridDim.x;
-      if (pt == 0 && tile < num_tiles) {
-        const int64_t r0 = tile * kTileM;
-        const int64_t rows = (p.M - r0) < kTileM ? (p.M - r0) : kTileM;
-        prefetch_l2_bulk(p.A + r0 * p.lda, (uint32_t)(((rows - 1) * p.lda + K) * 4));
-      }
-    };
-    for (int t = 1; t <= kL2Ahead; ++t) l2_prefetch_tile(t);
-    for (int64_t it0 = 0; it0 < total_kb; it0 += kPrefetch) {
-#pragma unroll
-      for (int slot = 0; slot < kPrefetch; ++slot) {  // compile-time slot: the prefetch buffers stay in registers
-        if (it0 + slot < total_kb) {
-          if ((it0 + slot) % kKBlocks == 0) l2_prefetch_tile((it0 + slot) / kKBlocks + kL2Ahead + 1);
-          MBAR_WAIT(bar_empty + 8 * stage, phase ^ 1);
-          if (dbg_ts && pt == 0 && it0 + slot < 256) dbg_ts[2 * (it0 + slot)] = clock64();
-          const uint32_t hi = sA + stage * L::kStageBytes;
-          const uint32_t lo = hi + L::kABlockBytes;
+      int stage = 0;
+      for (int64_t it = 0; it < total_kb; ++it) {
+        if (it % kKBlocks == 0) l2_prefetch_tile(it / kKBlocks + kL2Ahead + 1);
+        cp_async_wait<kCopyDepth - 1>();                      // this thread's copies of k-block `it` have landed
+        const uint32_t hi = sA + stage * L::kStageBytes;
+        const uint32_t lo = hi + L::kABlockBytes;
+        if (p.row_scale != nullptr) {
+          const int64_t tile = (int64_t)blockIdx.x + (it / kKBlocks) * gridDim.x;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            float4 v = buf[slot][i];
-            if (p.row_scale != nullptr) {
-              const float s = scale_buf[slot][i];
-              v.x = __fmul_rn(s, v.x); v.y = __fmul_rn(s, v.y); v.z = __fmul_rn(s, v.z); v.w = __fmul_rn(s, v.w);
+            const int64_t r = tile * kTileM + row0 + 32 * i;
+            const float sc = r < p.M ? __ldg(p.row_scale + r) : 1.0f;
+            float4 v = lds128(hi + offs[i]);
+            v.x = __fmul_rn(sc, v.x); v.y = __fmul_rn(sc, v.y); v.z = __fmul_rn(sc, v.z); v.w = __fmul_rn(sc, v.w);
+            sts128(hi + offs[i], v);
+            sts128(lo + offs[i], make_float4(tf32_trunc_residual(v.x), tf32_trunc_residual(v.y),
+                                             tf32_trunc_residual(v.z), tf32_trunc_residual(v.w)));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 v = lds128(hi + offs[i]);
+            sts128(lo + offs[i], make_float4(tf32_trunc_residual(v.x), tf32_trunc_residual(v.y),
+                                             tf32_trunc_residual(v.z), tf32_trunc_residual(v.w)));
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_full + 8 * stage);
+        if (++stage == kStages) stage = 0;
+        if (it + kCopyDepth < total_kb) issue(it + kCopyDepth);
+        cp_async_commit();
+      }
+    } else {
+      float4 buf[kPrefetch][4];
+      float scale_buf[kPrefetch][4];
+      int64_t it_load = 0;
+      auto load_block = [&](int64_t it, float4 (&dst)[4], float (&sc)[4]) {
+        const int64_t tile = (int64_t)blockIdx.x + (it / kKBlocks) * gridDim.x;
+        const int kb = (int)(it % kKBlocks);
+  #pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int64_t r = tile * kTileM + row0 + 32 * i;
+          if (r < p.M && !dbg_no_ldg) {
+            const float* src = p.A + r * p.lda + kb * kKB + c16 * 4;
+            float4 v;
+            asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                         : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(src));
+            dst[i] = v;
+            sc[i] = p.row_scale != nullptr ? __ldg(p.row_scale + r) : 1.0f;
+          } else {
+            dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            sc[i] = 1.0f;
+          }
+        }
+      };
+  #pragma unroll
+      for (int slot = 0; slot < kPrefetch; ++slot)
+        if (slot < total_kb) {
+          load_block(slot, buf[slot], scale_buf[slot]);
+          ++it_load;
+        }
+      int stage = 0;
+      uint32_t phase = 0;
+      constexpr int kL2Ahead = 3;  // tiles of this CTA kept on their way into L2
+      auto l2_prefetch_tile = [&](int64_t local_tile) {
+        // ONE thread, ONE bulk prefetch per tile (the tile's rows form one contiguous range of rows*lda floats).
+        // UBLKPF takes uniform operands: issued from many lanes the compiler serialises it lane by lane.
+        const int64_t tile = (int64_t)blockIdx.x + local_tile * gridDim.x;
+        if (pt == 0 && tile < num_tiles) {
+          const int64_t r0 = tile * kTileM;
+          const int64_t rows = (p.M - r0) < kTileM ? (p.M - r0) : kTileM;
+          prefetch_l2_bulk(p.A + r0 * p.lda, (uint32_t)(((rows - 1) * p.lda + K) * 4));
+        }
+      };
+      for (int t = 1; t <= kL2Ahead; ++t) l2_prefetch_tile(t);
+      for (int64_t it0 = 0; it0 < total_kb; it0 += kPrefetch) {
+  #pragma unroll
+        for (int slot = 0; slot < kPrefetch; ++slot) {  // compile-time slot: the prefetch buffers stay in registers
+          if (it0 + slot < total_kb) {
+            if ((it0 + slot) % kKBlocks == 0) l2_prefetch_tile((it0 + slot) / kKBlocks + kL2Ahead + 1);
+            MBAR_WAIT(bar_empty + 8 * stage, phase ^ 1);
+            if (dbg_ts && pt == 0 && it0 + slot < 256) dbg_ts[2 * (it0 + slot)] = clock64();
+            const uint32_t hi = sA + stage * L::kStageBytes;
+            const uint32_t lo = hi + L::kABlockBytes;
+  #pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float4 v = buf[slot][i];
+              if (p.row_scale != nullptr) {
+                const float s = scale_buf[slot][i];
+                v.x = __fmul_rn(s, v.x); v.y = __fmul_rn(s, v.y); v.z = __fmul_rn(s, v.z); v.w = __fmul_rn(s, v.w);
+              }
+              const uint32_t off = swz(row0 + 32 * i, c16);
+              if (!dbg_no_sts) split_store(hi + off, lo + off, v);
             }
-            const uint32_t off = swz(row0 + 32 * i, c16);
-            if (!dbg_no_sts) split_store(hi + off, lo + off, v);
+            // every writer fences its own generic-proxy stores towards the async proxy, the warp converges, and
+            // ONE lane arrives: 8 smem atomics per stage instead of 256 (the per-thread version cost 1.3 ms / 8 M rows)
+            if (!dbg_no_fence) fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_full + 8 * stage);
+            if (dbg_ts && pt == 0 && it0 + slot < 256) dbg_ts[2 * (it0 + slot) + 1] = clock64();
+            if (it_load < total_kb) {
+              load_block(it_load, buf[slot], scale_buf[slot]);
+              ++it_load;
+            }
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
-          // every writer fences its own generic-proxy stores towards the async proxy, the warp converges, and
-          // ONE lane arrives: 8 smem atomics per stage instead of 256 (the per-thread version cost 1.3 ms / 8 M rows)
-          if (!dbg_no_fence) fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_full + 8 * stage);
-          if (dbg_ts && pt == 0 && it0 + slot < 256) dbg_ts[2 * (it0 + slot) + 1] = clock64();
-          if (it_load < total_kb) {
-            load_block(it_load, buf[slot], scale_buf[slot]);
-            ++it_load;
-          }
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }

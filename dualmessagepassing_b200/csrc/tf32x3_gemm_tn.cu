@@ -73,7 +73,7 @@ __device__ __forceinline__ uint64_t smem_desc_mn32(uint32_t saddr, uint32_t lbo_
          ((uint64_t)1 << 46) | ((uint64_t)type << 61);
 }
 
-template <int M, int N>
+template <int M, int N, bool SX, bool SG>
 __global__ void __launch_bounds__(kTnThreads, 1) tf32x3_gemm_tn_kernel(const TnParams p) {
   using L = TnSmem<M, N>;
   extern __shared__ uint8_t smem_raw[];
@@ -126,11 +126,10 @@ __global__ void __launch_bounds__(kTnThreads, 1) tf32x3_gemm_tn_kernel(const TnP
     constexpr int kXChunks = kTnEdges * M / 4, kGChunks = kTnEdges * N / 4;
     constexpr int kXPer = kXChunks / kTnProducerThreads, kGPer = kGChunks / kTnProducerThreads;   // 4 (or 2)
     float4 bx[kTnPrefetch][kXPer], bg[kTnPrefetch][kGPer];
-    float sc[kTnPrefetch][kXPer];
     // bias gradients for free: a thread always handles the same 4 columns (256 % (M/4) == 0), so it keeps running
     // column sums of everything it streams; rows past E are zero-filled and add nothing
     float4 sum_x = make_float4(0.f, 0.f, 0.f, 0.f), sum_g = sum_x;
-    auto load_stage = [&](int64_t st, float4 (&dx)[kXPer], float4 (&dg)[kGPer], float (&s)[kXPer]) {
+    auto load_stage = [&](int64_t st, float4 (&dx)[kXPer], float4 (&dg)[kGPer]) {
       const int64_t e0 = (s_begin + st) * kTnEdges;
 #pragma unroll
       for (int i = 0; i < kXPer; ++i) {
@@ -140,10 +139,8 @@ __global__ void __launch_bounds__(kTnThreads, 1) tf32x3_gemm_tn_kernel(const TnP
           const float* src = p.X + e * p.ldx + (c % (M / 4)) * 4;
           asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                        : "=f"(dx[i].x), "=f"(dx[i].y), "=f"(dx[i].z), "=f"(dx[i].w) : "l"(src));
-          s[i] = p.row_scale != nullptr ? __ldg(p.row_scale + e) : 1.0f;
         } else {
           dx[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          s[i] = 1.0f;
         }
       }
 #pragma unroll
@@ -174,7 +171,7 @@ __global__ void __launch_bounds__(kTnThreads, 1) tf32x3_gemm_tn_kernel(const TnP
 #pragma unroll
     for (int slot = 0; slot < kTnPrefetch; ++slot)
       if (slot < n_stages) {
-        load_stage(slot, bx[slot], bg[slot], sc[slot]);
+        load_stage(slot, bx[slot], bg[slot]);
         ++st_load;
       }
     int stage = 0;
@@ -191,10 +188,13 @@ __global__ void __launch_bounds__(kTnThreads, 1) tf32x3_gemm_tn_kernel(const TnP
           for (int i = 0; i < kXPer; ++i) {
             const int c = pt + kTnProducerThreads * i;
             float4 v = bx[slot][i];
-            sum_x.x = __fadd_rn(sum_x.x, v.x); sum_x.y = __fadd_rn(sum_x.y, v.y);
-            sum_x.z = __fadd_rn(sum_x.z, v.z); sum_x.w = __fadd_rn(sum_x.w, v.w);
+            if constexpr (SX) {
+              sum_x.x = __fadd_rn(sum_x.x, v.x); sum_x.y = __fadd_rn(sum_x.y, v.y);
+              sum_x.z = __fadd_rn(sum_x.z, v.z); sum_x.w = __fadd_rn(sum_x.w, v.w);
+            }
             if (p.row_scale != nullptr) {
-              const float s = sc[slot][i];
+              const int64_t e = (s_begin + st0 + slot) * kTnEdges + c / (M / 4);
+              const float s = e < p.E ? __ldg(p.row_scale + e) : 1.0f;
               v.x = __fmul_rn(s, v.x); v.y = __fmul_rn(s, v.y); v.z = __fmul_rn(s, v.z); v.w = __fmul_rn(s, v.w);
             }
             const uint32_t off = swz_mn(c / (M / 4), c % (M / 4));
@@ -205,22 +205,24 @@ __global__ void __launch_bounds__(kTnThreads, 1) tf32x3_gemm_tn_kernel(const TnP
             const int c = pt + kTnProducerThreads * i;
             const uint32_t off = swz_mn(c / (N / 4), c % (N / 4));
             const float4 gv = bg[slot][i];
-            sum_g.x = __fadd_rn(sum_g.x, gv.x); sum_g.y = __fadd_rn(sum_g.y, gv.y);
-            sum_g.z = __fadd_rn(sum_g.z, gv.z); sum_g.w = __fadd_rn(sum_g.w, gv.w);
+            if constexpr (SG) {
+              sum_g.x = __fadd_rn(sum_g.x, gv.x); sum_g.y = __fadd_rn(sum_g.y, gv.y);
+              sum_g.z = __fadd_rn(sum_g.z, gv.z); sum_g.w = __fadd_rn(sum_g.w, gv.w);
+            }
             split_store(g_hi + off, g_lo + off, gv);
           }
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_full + 8 * stage);
           if (st_load < n_stages) {
-            load_stage(st_load, bx[slot], bg[slot], sc[slot]);
+            load_stage(st_load, bx[slot], bg[slot]);
             ++st_load;
           }
           if (++stage == kTnStages) { stage = 0; phase ^= 1; }
         }
       }
     }
-    if (p.part_sx != nullptr || p.part_sg != nullptr) {
+    if constexpr (SX || SG) {
       // threads with equal (pt % chunks-per-row) own the same columns: with 32 chunks per row that is one lane of each
       // of the 8 warps; with 16 chunks per row (64 features) lanes l and l+16 of every warp as well
       const int pw = pt >> 5;
@@ -234,15 +236,15 @@ __global__ void __launch_bounds__(kTnThreads, 1) tf32x3_gemm_tn_kernel(const TnP
         sum_g.x += __shfl_down_sync(0xffffffffu, sum_g.x, 16); sum_g.y += __shfl_down_sync(0xffffffffu, sum_g.y, 16);
         sum_g.z += __shfl_down_sync(0xffffffffu, sum_g.z, 16); sum_g.w += __shfl_down_sync(0xffffffffu, sum_g.w, 16);
       }
-      if (lane < M / 4) *reinterpret_cast<float4*>(sx + 4 * lane) = sum_x;
-      if (lane < N / 4) *reinterpret_cast<float4*>(sg + 4 * lane) = sum_g;
+      if (SX && lane < M / 4) *reinterpret_cast<float4*>(sx + 4 * lane) = sum_x;
+      if (SG && lane < N / 4) *reinterpret_cast<float4*>(sg + 4 * lane) = sum_g;
       asm volatile("bar.sync 1, %0;" ::"n"(kTnProducerThreads) : "memory");
-      if (pt < M && p.part_sx != nullptr) {
+      if (SX && pt < M) {
         float t = 0.0f;
         for (int w = 0; w < kTnProducerWarps; ++w) t = __fadd_rn(t, sum_scratch[w * 128 + pt]);
         p.part_sx[(int64_t)blockIdx.x * M + pt] = t;
       }
-      if (pt < N && p.part_sg != nullptr) {
+      if (SG && pt < N) {
         float t = 0.0f;
         for (int w = 0; w < kTnProducerWarps; ++w) t = __fadd_rn(t, sum_scratch[(kTnProducerWarps + w) * 128 + pt]);
         p.part_sg[(int64_t)blockIdx.x * N + pt] = t;
@@ -355,20 +357,29 @@ __global__ void __launch_bounds__(256) tn_reduce_kernel(const float* __restrict_
   *d = accumulate ? __fadd_rn(*d, s) : s;
 }
 
-template <int M, int N>
-static int launch_tn(const TnParams& p, unsigned grid, cudaStream_t stream) {
+template <int M, int N, bool SX, bool SG>
+static int launch_tn_s(const TnParams& p, unsigned grid, cudaStream_t stream) {
   using L = TnSmem<M, N>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tf32x3_gemm_tn_kernel<M, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    cudaError_t e = cudaFuncSetAttribute(tf32x3_gemm_tn_kernel<M, N, SX, SG>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
     if (e != cudaSuccess) {
       set_error("gemm_tn_tf32x3: cannot reserve %d bytes of shared memory: %s", L::kTotal, cudaGetErrorString(e));
       return DMP_ERR_CUDA;
     }
     configured = true;
   }
-  tf32x3_gemm_tn_kernel<M, N><<<grid, kTnThreads, L::kTotal, stream>>>(p);
+  tf32x3_gemm_tn_kernel<M, N, SX, SG><<<grid, kTnThreads, L::kTotal, stream>>>(p);
   return launch_status("tf32x3_gemm_tn_kernel");
+}
+
+template <int M, int N>
+static int launch_tn(const TnParams& p, unsigned grid, cudaStream_t stream) {
+  const bool sx = p.part_sx != nullptr, sg = p.part_sg != nullptr;
+  if (sx && sg) return launch_tn_s<M, N, true, true>(p, grid, stream);
+  if (sx) return launch_tn_s<M, N, true, false>(p, grid, stream);
+  if (sg) return launch_tn_s<M, N, false, true>(p, grid, stream);
+  return launch_tn_s<M, N, false, false>(p, grid, stream);
 }
 
 }  // namespace gemm
