@@ -191,7 +191,7 @@ def kernel_bytes(tag, N, E, H, has_norm=False):
     if tag == "edge_update":
         return 5 * E * row + 12 * E + row
     if tag == "edge_backward":
-        return 4 * E * row + 9 * E
+        return 2 * E * row + 5 * E   # gather gN[dst] + write T (coef*gE is folded into the GEMM prologues)
     if tag == "act_inplace":
         return None  # rows differ (node / edge); filled by caller
     return None
@@ -367,12 +367,16 @@ def run_ours(args):
     value = E / (ms_per_step * 1e-3)
 
     # ---- per-kernel durations -> roofline of the dominant hand-written kernel ----------------------------
-    by_tag = {}
-    for tag, e_0, e_1 in prof:
+    by_tag, bytes_by_tag = {}, {}
+    for tag, e_0, e_1, nb in prof:
         by_tag.setdefault(tag, []).append(e_0.elapsed_time(e_1))
+        if nb is not None:
+            bytes_by_tag[tag] = bytes_by_tag.get(tag, 0) + nb
     kernels = {}
     for tag, ms in by_tag.items():
-        nb = kernel_bytes(tag, nN, nE, h)
+        # algorithmic bytes: fixed-shape kernels from the table in DESIGN.md, GEMM launches report their own
+        # (operands + result, shapes differ per launch) -> average bytes per launch
+        nb = bytes_by_tag[tag] / len(ms) if tag in bytes_by_tag else kernel_bytes(tag, nN, nE, h)
         avg = float(np.mean(ms))
         entry = {"launches_per_step": len(ms) / args.steps, "avg_ms": avg, "share_of_step": sum(ms) / total_ms}
         if nb is not None:
@@ -388,8 +392,15 @@ def run_ours(args):
         roofline = {"kernel": top, "bound": "hbm", "achieved": kv["gbs"], "peak": hbm_peak, "unit": "GB/s",
                     "frac": kv["frac"], "traffic": None, "alg_bytes_per_launch": kv["alg_bytes"],
                     "avg_launch_ms": kv["avg_ms"], "peak_source": peak_src}
-        sparse_ms = sum(v["avg_ms"] * v["launches_per_step"] for v in cand.values())
-        sparse_bytes = sum(v["alg_bytes"] * v["launches_per_step"] for v in cand.values())
+        sp = {k: v for k, v in cand.items() if not k.startswith("gemm")}
+        sparse_ms = sum(v["avg_ms"] * v["launches_per_step"] for v in sp.values())
+        sparse_bytes = sum(v["alg_bytes"] * v["launches_per_step"] for v in sp.values())
+        dense = {k: v for k, v in cand.items() if k.startswith("gemm")}
+        if dense:
+            d_ms = sum(v["avg_ms"] * v["launches_per_step"] for v in dense.values())
+            d_b = sum(v["alg_bytes"] * v["launches_per_step"] for v in dense.values())
+            roofline["dense_tf32x3"] = {"ms_per_step": d_ms, "alg_bytes_per_step": d_b, "gbs": d_b / (d_ms * 1e-3) / 1e9,
+                                        "frac": d_b / (d_ms * 1e-3) / 1e9 / hbm_peak}
         roofline["sparse_core"] = {"ms_per_step": sparse_ms, "alg_bytes_per_step": sparse_bytes,
                                    "gbs": sparse_bytes / (sparse_ms * 1e-3) / 1e9,
                                    "frac": sparse_bytes / (sparse_ms * 1e-3) / 1e9 / hbm_peak,

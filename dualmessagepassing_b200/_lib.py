@@ -73,11 +73,11 @@ def check(rc, what):
 
 
 # ---- optional per-launch timing (bench.py): CUDA events on the launching stream around every C-ABI call
-PROFILE = None   # None = off; else list of (tag, start_event, end_event)
+PROFILE = None   # None = off; else list of (tag, start_event, end_event, algorithmic bytes or None)
 LAUNCHES = 0     # number of C-ABI kernel-launching calls made so far (bench.py reports the delta)
 
 
-def call(name, device, *args, tag=None):
+def call(name, device, *args, tag=None, nbytes=None):
     """Invoke one entry point on `device`'s current stream; raise on a non-zero status."""
     global LAUNCHES
     lib = load()
@@ -89,7 +89,7 @@ def call(name, device, *args, tag=None):
             e0.record(stream)
             rc = getattr(lib, name)(*args)
             e1.record(stream)
-            PROFILE.append((tag or name, e0, e1))
+            PROFILE.append((tag or name, e0, e1, nbytes))
         else:
             rc = getattr(lib, name)(*args)
     LAUNCHES += 1

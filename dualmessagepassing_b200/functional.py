@@ -223,7 +223,8 @@ def gemm_tf32x3(A, Wt, *, row_scale=None, bias=None, act="none", slope=0.0, aux=
         bias = bias.contiguous()
     _lib.call("dmp_gemm_tf32x3", A.device, _lib.ptr(A), lda, _lib.ptr(row_scale), _lib.ptr(Wt), ldb,
               _lib.ptr(bias), _lib.ptr(aux if mul_act_grad else None), ld_aux, _lib.ptr(out), ldd, M, N, K, epi,
-              float(slope), _stream(A), tag="gemm_tf32x3")
+              float(slope), _stream(A), tag="gemm_tf32x3",
+              nbytes=4 * (M * K + M * N * (2 if accumulate else 1) + (M * N if mul_act_grad else 0) + N * K))
     return out
 
 
@@ -258,7 +259,7 @@ def gemm_tn_tf32x3(X, G, *, row_scale=None, out=None, accumulate=False, colsum_x
     sg = torch.empty(N, dtype=torch.float32, device=X.device) if colsum_g else None
     _lib.call("dmp_gemm_tn_tf32x3", X.device, _lib.ptr(X), ldx, _lib.ptr(row_scale), _lib.ptr(G), ldg, _lib.ptr(out),
               ldd, _lib.ptr(sx), _lib.ptr(sg), E, M, N, int(accumulate), _lib.ptr(ws), ws.numel(), _stream(X),
-              tag="gemm_tn_tf32x3")
+              tag="gemm_tn_tf32x3", nbytes=4 * (E * M + E * N + M * N) + (4 * E if row_scale is not None else 0))
     if colsum_x or colsum_g:
         return out, sx, sg
     return out
