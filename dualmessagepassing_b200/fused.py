@@ -54,8 +54,13 @@ DENSE_BACKEND = "auto"
 _ACT_NAME = {v: k for k, v in _ACT.items()}
 
 
+# below this many rows the persistent tcgen05 kernels' fixed cost (weight split per CTA, TMEM allocation, second
+# reduce launch) exceeds what cuBLAS sgemm needs for the whole product
+TC_MIN_ROWS = 16384
+
+
 def _use_tc(A, Wt):
-    return (DENSE_BACKEND == "auto" and A.dtype == torch.float32 and A.shape[0] > 0
+    return (DENSE_BACKEND == "auto" and A.dtype == torch.float32 and A.shape[0] >= TC_MIN_ROWS
             and Wt.shape[0] in (64, 128) and Wt.shape[1] in (64, 128)
             and A.stride(1) == 1 and A.stride(0) % 4 == 0 and A.data_ptr() % 16 == 0)
 
@@ -88,7 +93,7 @@ def _tnmm(X, G, *, row_scale=None, colsum_x=False, colsum_g=False):
     """(row_scale ⊙ X).T @ G -- the K = rows long weight-gradient reduction; tensor cores when both widths allow.
     colsum_x / colsum_g: also return X.sum(0) / G.sum(0) (bias gradients) -> (D, sum_x, sum_g)."""
     want_sums = colsum_x or colsum_g
-    if (DENSE_BACKEND == "auto" and X.shape[0] > 0 and X.shape[1] in (64, 128) and G.shape[1] in (64, 128)
+    if (DENSE_BACKEND == "auto" and X.shape[0] >= TC_MIN_ROWS and X.shape[1] in (64, 128) and G.shape[1] in (64, 128)
             and X.stride(1) == 1 and G.stride(1) == 1 and X.stride(0) % 4 == 0 and G.stride(0) % 4 == 0
             and X.data_ptr() % 16 == 0 and G.data_ptr() % 16 == 0):
         return gemm_tn_tf32x3(X, G, row_scale=row_scale, colsum_x=colsum_x, colsum_g=colsum_g)
@@ -143,7 +148,7 @@ class _FusedDMPLayer(torch.autograd.Function):
         if plan.rev_layout == "none":
             M, m_off = _rowmm(X_e, in_t), 0
         elif plan.rev_layout == "halves":
-            h = E // 2
+            h = plan.rev_split
             M, m_off = torch.empty((E, H), dtype=X_e.dtype, device=X_e.device), 0
             _rowmm(X_e[:h], in_t, out=M[:h])
             _rowmm(X_e[h:], out_t, out=M[h:])
@@ -257,7 +262,7 @@ class _FusedDMPLayer(torch.autograd.Function):
             if plan.rev_layout == "none":
                 _rowmm(T, in_w, out=dX_e, accumulate=True)
             elif plan.rev_layout == "halves":
-                h = E // 2
+                h = plan.rev_split
                 _rowmm(T[:h], in_w, out=dX_e[:h], accumulate=True)
                 _rowmm(T[h:], out_w, out=dX_e[h:], accumulate=True)
             else:
@@ -280,7 +285,7 @@ class _FusedDMPLayer(torch.autograd.Function):
                 d_in = _tnmm(X_e, T)
                 d_out = torch.zeros_like(out_w)
             elif plan.rev_layout == "halves":
-                h = E // 2
+                h = plan.rev_split
                 d_in = _tnmm(X_e[:h], T[:h])
                 d_out = _tnmm(X_e[h:], T[h:])
             else:

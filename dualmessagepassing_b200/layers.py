@@ -77,7 +77,7 @@ def dual_message_passing(plan, node_feat, edge_feat, in_weight, out_weight, src_
     if plan.rev_layout == "none":
         M = X_e @ in_weight
     elif plan.rev_layout == "halves":
-        M = _SplitMM.apply(X_e, in_weight, out_weight, plan.E // 2)
+        M = _SplitMM.apply(X_e, in_weight, out_weight, plan.rev_split)
     else:
         M = X_e @ torch.cat([in_weight, out_weight], dim=1)  # [E, 2H]: branch picked inside the kernel
         m_rev_off = H

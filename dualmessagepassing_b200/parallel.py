@@ -119,14 +119,15 @@ class PartitionedDMPLayer:
         self.local_E = int(part["eids"].size)
         t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)  # noqa: E731
         r = part["rev"]
-        layout = None
-        if r is not None and self.local_E % 2 == 0 and self.local_E > 0:
-            h = self.local_E // 2
-            if (not r[:h].any()) and r[h:].all():
-                layout = "halves"
+        layout, split = None, None
+        if r is not None and self.local_E > 0:
+            # a destination-range slice of a [forward | reversed] edge list is again [forward | reversed]
+            n_fwd = int((~r.astype(bool)).sum())
+            if (not r[:n_fwd].any()) and r[n_fwd:].all():
+                layout, split = "halves", n_fwd
         self.plan = DMPPlan(t(part["src"]), t(part["dst"]), self.N,
                             rev=None if r is None else t(r.astype(np.uint8)), out_deg=t(part["out_deg"]),
-                            rev_layout=layout)
+                            rev_layout=layout, rev_split=split)
 
     def __call__(self, node_feat_local, edge_feat_local):
         L = self.layer

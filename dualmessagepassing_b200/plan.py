@@ -29,7 +29,7 @@ def _coef_lut(device):
 class DMPPlan:
     """Index structures of one graph (all int32 on device; layout in DESIGN.md)."""
 
-    def __init__(self, src, dst, num_nodes, rev=None, out_deg=None, validate=True, rev_layout=None):
+    def __init__(self, src, dst, num_nodes, rev=None, out_deg=None, validate=True, rev_layout=None, rev_split=None):
         _lib.require_cuda(src, dst, rev, out_deg)
         lib = _lib.load()
         dev = src.device
@@ -75,7 +75,8 @@ class DMPPlan:
                 _lib.ptr(status), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)), "dmp_plan_build")
         # Layout of the reversed flags decides how the node-message projection is issued (layers.py):
         #   "none"    no flags                    -> one GEMM with W_in
-        #   "halves"  [forward E/2 | reversed E/2] (add_reversed_edges on a single graph) -> two GEMMs
+        #   "halves"  [forward block | reversed block], split at `rev_split` (E/2 after add_reversed_edges on a
+        #             single graph; any split point for a partition of such a graph) -> two GEMMs
         #   "general" anything else (e.g. batched graphs: per-graph blocks) -> one [E, 2H] two-branch GEMM
         if self.rev is None:
             self.rev_layout = "none"
@@ -83,17 +84,20 @@ class DMPPlan:
             self.rev_layout = rev_layout
         else:
             self.rev_layout = "general"
+        self.rev_split = E // 2 if rev_split is None else int(rev_split)
         if validate:
             # one small D2H read per plan: endpoint range check (+ layout detection when not hinted)
-            if self.rev is not None and rev_layout is None and E > 0 and E % 2 == 0:
-                h = E // 2
-                halves = (~self.rev[:h].any()) & self.rev[h:].all()
-                status[1] = halves.to(torch.int32)
+            if self.rev is not None and rev_layout is None and E > 0:
+                # [forward block | reversed block] <=> the flags are sorted; the split point is the forward count
+                n_fwd = (self.rev == 0).sum()
+                is_sorted = (self.rev[1:] >= self.rev[:-1]).all() if E > 1 else torch.ones((), dtype=torch.bool, device=dev)
+                status[1] = torch.where(is_sorted, n_fwd + 1, torch.zeros_like(n_fwd)).to(torch.int32)
             st = status.tolist()
             if st[0] != 0:
                 raise ValueError("graph has an edge endpoint outside [0, num_nodes)")
             if st[1] != 0:
                 self.rev_layout = "halves"
+                self.rev_split = st[1] - 1
         self._norm_perm = {}
         del ws
 

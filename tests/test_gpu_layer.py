@@ -21,6 +21,17 @@ pytestmark = pytest.mark.gpu
 RTOL, ATOL = 1e-5, 1e-6
 
 
+@pytest.fixture(autouse=True)
+def _tensor_core_path_at_test_sizes():
+    """Production routes projections with < 16384 rows to cuBLAS (fixed cost of the persistent tcgen05 kernels);
+    the tests are small, so lower the threshold to keep the tensor-core path under test."""
+    from dualmessagepassing_b200 import fused
+    old = fused.TC_MIN_ROWS
+    fused.TC_MIN_ROWS = 1
+    yield
+    fused.TC_MIN_ROWS = old
+
+
 def close(got, want, name, scale_atol=True):
     want = want.to(torch.float32)
     atol = ATOL * max(1.0, float(want.abs().max())) if scale_atol else ATOL

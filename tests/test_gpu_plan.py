@@ -39,7 +39,7 @@ def test_plan_bit_exact(name, kw):
     plan = DMPPlan(t(s), t(d), n, rev=t(None if r is None else r.astype(np.uint8)))
     _check(plan, go.build_plan(s, d, n, r), r)
     if kw["rev"] == "halves":
-        assert plan.rev_layout == "halves"
+        assert plan.rev_layout == "halves" and plan.rev_split == len(s) // 2
     elif kw["rev"] == "shuffled":
         assert plan.rev_layout == "general"
     else:
