@@ -47,10 +47,13 @@ def _worker(rank, world, port, q):
     nv2, ne2 = runner(a2, b2)
     torch.autograd.backward((nv2, ne2), (gv[lo:hi], ge[ids]))
     torch.cuda.synchronize()
-    ok = torch.equal(nv2, nv[lo:hi]) and torch.equal(ne2, ne[ids])  # same sums in the same order
+    # The sparse core keeps the single-GPU summation order, and the tensor-core projections are row-independent;
+    # the node-sized projections below 16k rows run on cuBLAS, whose kernel choice depends on the row count
+    # (3000 vs 1500 here), so the forward is compared at fp32 tolerance rather than bit for bit.
     msgs = []
-    if not ok:
-        msgs.append("forward differs: %g %g" % (float((nv2 - nv[lo:hi]).abs().max()), float((ne2 - ne[ids]).abs().max())))
+    for name, x, y in (("node_out", nv2, nv[lo:hi]), ("edge_out", ne2, ne[ids])):
+        if not torch.allclose(x, y, rtol=1e-5, atol=1e-5 * max(1.0, float(y.abs().max()))):
+            msgs.append("forward %s differs: %g" % (name, float((x - y).abs().max())))
 
     def chk(name, x, y, rtol=1e-4, scale=1e-5):
         atol = scale * max(1.0, float(y.abs().max()))
