@@ -16,6 +16,8 @@ LIB_PATH = os.path.join(_HERE, "libdmp_b200.so")
 EID_MASK = 0x7FFFFFFF
 SEG_SIGN_BY_REV = 1
 SEG_NEGATE_OUT = 2
+SEG_ONLY_FWD = 4
+SEG_ONLY_REV = 8
 ORDER_SCM = 0
 ORDER_UNC = 1
 ACT_NONE, ACT_RELU, ACT_LEAKY_RELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3, 4
@@ -38,6 +40,8 @@ SIGNATURES = {
     "dmp_edge_backward": [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _i64, _vp],
     "dmp_gate_residual": [_vp, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i32, _f32, _vp],
     "dmp_gate_residual_backward": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _i32, _f32, _vp],
+    "dmp_gemm_tf32x3_acc_gather": [_vp, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp,
+                                   _i64, _vp],
     "dmp_gemm_tn_workspace_bytes": [_i64, _i64, ctypes.POINTER(ctypes.c_int64)],
     "dmp_gemm_tn_tf32x3": [_vp, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _i32, _vp, _i64, _vp],
     "dmp_gemm_tf32x3": [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _i32, _f32, _vp],

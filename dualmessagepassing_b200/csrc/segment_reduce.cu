@@ -41,6 +41,8 @@ __global__ void __launch_bounds__(kThreads) segment_reduce_kernel(const SegParam
   const int end = __ldg(p.indptr + seg + 1);
   const bool sign_by_rev = (p.mode & DMP_SEG_SIGN_BY_REV) != 0;
   const bool has_w = p.w_perm != nullptr;
+  // edge filter by the reversed flag (bit 31): keep = flag XOR-matches; filtered rows are never loaded
+  const uint32_t filt = (p.mode & (DMP_SEG_ONLY_FWD | DMP_SEG_ONLY_REV));
 
   int col[ITER];
   bool ok[ITER];
@@ -68,7 +70,10 @@ __global__ void __launch_bounds__(kThreads) segment_reduce_kernel(const SegParam
     Row<VEC> v[U][ITER];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      if (j + u < end) {
+      const bool keep = (j + u < end) && !((filt & DMP_SEG_ONLY_FWD) && (ef[u] >> 31)) &&
+                        !((filt & DMP_SEG_ONLY_REV) && !(ef[u] >> 31));
+      if (!keep) ef[u] = 0xffffffffu;   // sentinel: (id mask, rev) can never both be all-ones for a real edge
+      if (keep) {
         const uint32_t r = ef[u] >> 31;
         const float* row = p.V + (int64_t)(ef[u] & DMP_EID_MASK) * p.ldV + (r ? p.rev_off : 0);
 #pragma unroll
@@ -78,7 +83,7 @@ __global__ void __launch_bounds__(kThreads) segment_reduce_kernel(const SegParam
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      if (j + u < end) {
+      if (j + u < end && ef[u] != 0xffffffffu) {
         const bool neg = sign_by_rev && (ef[u] >> 31) == 0;
 #pragma unroll
         for (int it = 0; it < ITER; ++it) {

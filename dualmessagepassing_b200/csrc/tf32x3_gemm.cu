@@ -62,6 +62,13 @@ struct GemmParams {
   int64_t M;
   int epilogue;
   float slope;
+  // kModeAccGather: D += acc + sgn_r * norm_r * tab_{rev_r}[dst32[r], :]
+  const int32_t* g_dst;
+  const uint8_t* g_rev;
+  const float* g_norm;
+  const float* g_tab0;
+  const float* g_tab1;
+  int64_t ld_tab;
 };
 
 template <int N, int K>
@@ -89,12 +96,13 @@ enum : int {
   kModeGradPwl = 3,      // D = acc * (aux > 0 ? 1 : slope)
   kModeBiasSmooth = 4,   // D = tanh|sigmoid(acc + bias)
   kModeGradSmooth = 5,   // D = acc * d tanh|sigmoid expressed through aux = activation output
+  kModeAccGather = 6,    // D += acc + sgn_r * norm_r * table_{rev_r}[dst_r, :]   (backward of fn.sum folded into dX_e)
 };
 
 template <int MODE>
 __device__ __forceinline__ float epilogue_op(float acc, float bias, float aux, float old, float slope, int act) {
   if constexpr (MODE == kModeStore) return acc;
-  if constexpr (MODE == kModeAccumulate) return __fadd_rn(old, acc);
+  if constexpr (MODE == kModeAccumulate || MODE == kModeAccGather) return __fadd_rn(old, acc);
   if constexpr (MODE == kModeBiasPwl) {
     const float x = __fadd_rn(acc, bias);
     return x > 0.0f ? x : __fmul_rn(x, slope);
@@ -444,18 +452,41 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) tf32x3_gemm_kernel(const Gemm
               // operands of the epilogue (previous D for accumulate, activation output for act') are fetched as
               // 32 independent loads BEFORE the first store: one latency per chunk instead of one per row
               float t[32];
-              if constexpr (kNeedAux || MODE == kModeAccumulate) {
+              if constexpr (kNeedAux || MODE == kModeAccumulate || MODE == kModeAccGather) {
                 const float* src = kNeedAux ? aux : dst;
                 const int64_t lds = kNeedAux ? p.ld_aux : p.ldd;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) t[j] = src[j * lds];
               }
+              if constexpr (MODE == kModeAccGather) {
+                // row metadata: lane j fetches row r0+j (one coalesced load each), broadcast by shuffle in the loop
+                const int d_l = __ldg(p.g_dst + r0 + lane);
+                const int rv_l = p.g_rev != nullptr ? (int)__ldg(p.g_rev + r0 + lane) : 0;
+                const float w_l = p.g_norm != nullptr ? __ldg(p.g_norm + r0 + lane) : 1.0f;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float y = kNeedAux ? t[j] : 0.0f;
-                const float old = (MODE == kModeAccumulate) ? t[j] : 0.0f;
-                *dst = epilogue_op<MODE>(v[c][j], bias_f, y, old, p.slope, act);
-                dst += p.ldd;
+                for (int j = 0; j < 32; ++j) v[c][j] = __fadd_rn(t[j], v[c][j]);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  const int d = __shfl_sync(0xffffffffu, d_l, j);
+                  const int rv = __shfl_sync(0xffffffffu, rv_l, j);
+                  t[j] = __ldg((rv ? p.g_tab1 : p.g_tab0) + (int64_t)d * p.ld_tab + f);
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  const int rv = __shfl_sync(0xffffffffu, rv_l, j);
+                  float x = t[j];
+                  if (p.g_norm != nullptr) x = __fmul_rn(x, __shfl_sync(0xffffffffu, w_l, j));
+                  *dst = __fadd_rn(v[c][j], rv ? x : -x);
+                  dst += p.ldd;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  const float y = kNeedAux ? t[j] : 0.0f;
+                  const float old = (MODE == kModeAccumulate) ? t[j] : 0.0f;
+                  *dst = epilogue_op<MODE>(v[c][j], bias_f, y, old, p.slope, act);
+                  dst += p.ldd;
+                }
               }
             }
           } else {
@@ -464,8 +495,16 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) tf32x3_gemm_kernel(const Gemm
             for (int j = 0; j < 32; ++j) {
               if (j < nvalid) {
                 const float y = kNeedAux ? aux[j * p.ld_aux] : 0.0f;
-                const float old = (MODE == kModeAccumulate) ? dst[j * p.ldd] : 0.0f;
-                dst[j * p.ldd] = epilogue_op<MODE>(v[c][j], bias_f, y, old, p.slope, act);
+                const float old = (MODE == kModeAccumulate || MODE == kModeAccGather) ? dst[j * p.ldd] : 0.0f;
+                float o = epilogue_op<MODE>(v[c][j], bias_f, y, old, p.slope, act);
+                if constexpr (MODE == kModeAccGather) {
+                  const int64_t r = r0 + j;
+                  const int rv = p.g_rev != nullptr ? (int)__ldg(p.g_rev + r) : 0;
+                  float x = __ldg((rv ? p.g_tab1 : p.g_tab0) + (int64_t)__ldg(p.g_dst + r) * p.ld_tab + f);
+                  if (p.g_norm != nullptr) x = __fmul_rn(x, __ldg(p.g_norm + r));
+                  o = __fadd_rn(o, rv ? x : -x);
+                }
+                dst[j * p.ldd] = o;
               }
             }
           }
@@ -487,11 +526,22 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) tf32x3_gemm_kernel(const Gemm
               float4 b = make_float4(0.f, 0.f, 0.f, 0.f), y = b, d = b, o;
               if (kNeedBias && p.bias != nullptr) b = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + 4 * q));
               if (kNeedAux) y = *reinterpret_cast<const float4*>(arow + 4 * q);
-              if (MODE == kModeAccumulate) d = *reinterpret_cast<const float4*>(drow + 4 * q);
+              if (MODE == kModeAccumulate || MODE == kModeAccGather) d = *reinterpret_cast<const float4*>(drow + 4 * q);
               o.x = epilogue_op<MODE>(v[4 * q + 0], b.x, y.x, d.x, p.slope, act);
               o.y = epilogue_op<MODE>(v[4 * q + 1], b.y, y.y, d.y, p.slope, act);
               o.z = epilogue_op<MODE>(v[4 * q + 2], b.z, y.z, d.z, p.slope, act);
               o.w = epilogue_op<MODE>(v[4 * q + 3], b.w, y.w, d.w, p.slope, act);
+              if constexpr (MODE == kModeAccGather) {
+                const int rv = p.g_rev != nullptr ? (int)__ldg(p.g_rev + r) : 0;
+                float4 x = __ldg(reinterpret_cast<const float4*>((rv ? p.g_tab1 : p.g_tab0) +
+                                                                 (int64_t)__ldg(p.g_dst + r) * p.ld_tab + c0 + 4 * q));
+                if (p.g_norm != nullptr) {
+                  const float w = __ldg(p.g_norm + r);
+                  x.x = __fmul_rn(x.x, w); x.y = __fmul_rn(x.y, w); x.z = __fmul_rn(x.z, w); x.w = __fmul_rn(x.w, w);
+                }
+                o.x = __fadd_rn(o.x, rv ? x.x : -x.x); o.y = __fadd_rn(o.y, rv ? x.y : -x.y);
+                o.z = __fadd_rn(o.z, rv ? x.z : -x.z); o.w = __fadd_rn(o.w, rv ? x.w : -x.w);
+              }
               *reinterpret_cast<float4*>(drow + 4 * q) = o;
             }
           }
@@ -538,6 +588,7 @@ static int launch_gemm(const GemmParams& p, int mode, cudaStream_t stream) {
     case kModeBiasPwl: return launch_gemm_mode<N, K, kModeBiasPwl>(p, stream);
     case kModeGradPwl: return launch_gemm_mode<N, K, kModeGradPwl>(p, stream);
     case kModeBiasSmooth: return launch_gemm_mode<N, K, kModeBiasSmooth>(p, stream);
+    case kModeAccGather: return launch_gemm_mode<N, K, kModeAccGather>(p, stream);
     default: return launch_gemm_mode<N, K, kModeGradSmooth>(p, stream);
   }
 }
@@ -572,6 +623,7 @@ extern "C" int dmp_gemm_tf32x3(const float* A, int64_t lda, const float* row_sca
   GemmParams p;
   p.A = A; p.lda = lda; p.row_scale = row_scale; p.Bt = Bt; p.ldb = ldb; p.bias = bias;
   p.aux = aux; p.ld_aux = ld_aux; p.D = D; p.ldd = ldd; p.M = M; p.epilogue = epilogue; p.slope = slope;
+  p.g_dst = nullptr; p.g_rev = nullptr; p.g_norm = nullptr; p.g_tab0 = p.g_tab1 = nullptr; p.ld_tab = 0;
   const bool smooth = (act == DMP_ACT_TANH || act == DMP_ACT_SIGMOID);
   if (act == DMP_ACT_NONE) p.slope = 1.0f;   // piecewise-linear family: none = slope 1, relu = slope 0
   if (act == DMP_ACT_RELU) p.slope = 0.0f;
@@ -586,4 +638,34 @@ extern "C" int dmp_gemm_tf32x3(const float* A, int64_t lda, const float* row_sca
   if (N == 128 && K == 64) return launch_gemm<128, 64>(p, mode, s);
   if (N == 64 && K == 128) return launch_gemm<64, 128>(p, mode, s);
   return launch_gemm<64, 64>(p, mode, s);
+}
+
+extern "C" int dmp_gemm_tf32x3_acc_gather(const float* A, int64_t lda, const float* row_scale, const float* Bt,
+                                          int64_t ldb, float* D, int64_t ldd, int64_t M, int64_t N, int64_t K,
+                                          const int32_t* dst32, const uint8_t* rev, const float* norm,
+                                          const float* tab_fwd, const float* tab_rev, int64_t ld_tab, void* stream) {
+  using namespace dmp;
+  using namespace dmp::gemm;
+  DMP_CHECK_ARG(M >= 0, "gemm_acc_gather: negative M");
+  if (M == 0) return DMP_OK;
+  DMP_CHECK_ARG(A && Bt && D && dst32 && tab_fwd, "gemm_acc_gather: null pointer");
+  DMP_CHECK_ARG(rev == nullptr || tab_rev != nullptr, "gemm_acc_gather: reversed edges need tab_rev");
+  DMP_CHECK_ARG((N == 64 || N == 128) && (K == 64 || K == 128), "gemm_acc_gather: N and K must be 64 or 128");
+  DMP_CHECK_ARG(lda >= K && ldb >= K && ldd >= N && ld_tab >= N && lda % 4 == 0 && ldb % 4 == 0 && ldd % 4 == 0 &&
+                    ld_tab % 4 == 0,
+                "gemm_acc_gather: leading dimensions must be >= the row length and multiples of 4");
+  DMP_CHECK_ARG(aligned_to(A, 16) && aligned_to(Bt, 16) && aligned_to(D, 16) && aligned_to(tab_fwd, 16) &&
+                    aligned_to(tab_rev, 16),
+                "gemm_acc_gather: operands must be 16-byte aligned");
+  DMP_CHECK_ARG(A != D, "gemm_acc_gather: D must not alias A");
+  GemmParams p;
+  p.A = A; p.lda = lda; p.row_scale = row_scale; p.Bt = Bt; p.ldb = ldb; p.bias = nullptr;
+  p.aux = nullptr; p.ld_aux = 0; p.D = D; p.ldd = ldd; p.M = M; p.epilogue = 0; p.slope = 1.0f;
+  p.g_dst = dst32; p.g_rev = rev; p.g_norm = norm; p.g_tab0 = tab_fwd; p.g_tab1 = tab_rev ? tab_rev : tab_fwd;
+  p.ld_tab = ld_tab;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (N == 128 && K == 128) return launch_gemm<128, 128>(p, kModeAccGather, s);
+  if (N == 128 && K == 64) return launch_gemm<128, 64>(p, kModeAccGather, s);
+  if (N == 64 && K == 128) return launch_gemm<64, 128>(p, kModeAccGather, s);
+  return launch_gemm<64, 64>(p, kModeAccGather, s);
 }

@@ -16,7 +16,8 @@ Reference lines: SubgraphCountingMatching/models/dmpnn.py:111-156 (forward), SUR
 import torch
 
 from . import _lib
-from .functional import edge_backward, edge_update, gemm_tf32x3, gemm_tn_tf32x3, segment_reduce
+from .functional import (edge_backward, edge_update, gemm_tf32x3, gemm_tf32x3_acc_gather, gemm_tn_tf32x3,
+                         segment_reduce)
 
 _ACT = {"none": _lib.ACT_NONE, "relu": _lib.ACT_RELU, "leaky_relu": _lib.ACT_LEAKY_RELU,
         "tanh": _lib.ACT_TANH, "sigmoid": _lib.ACT_SIGMOID}
@@ -179,6 +180,7 @@ class _FusedDMPLayer(torch.autograd.Function):
             edge_out, eh1 = _act_inplace(edge_pre, act, slope), None
             node_pre = edge_pre = None
         ctx.plan, ctx.cfg, ctx.norm_flat, ctx.m_off, ctx.part = plan, cfg, norm_flat, m_off, part
+        ctx.norm_perm = norm_perm
         ctx.X_v_full = X_v_full if part is not None else None
         ctx.save_for_backward(X_v, X_e, in_w, out_w, src_w, dst_w, nloop_w, eloop_w, nW1, nW2, eW1, eW2,
                               node_pre, nh1, edge_pre, eh1,
@@ -229,20 +231,25 @@ class _FusedDMPLayer(torch.autograd.Function):
         dQd = segment_reduce(plan.a_indptr, plan.a_eid, gE, H, tag="segment_reduce.dQd_bwd")
         dQs = segment_reduce(plan.b_indptr, plan.b_eid, gE, H, mode=_lib.SEG_NEGATE_OUT,
                              tag="segment_reduce.dQs_bwd")
-        m_cols = H + ctx.m_off
-        if buf is not None and ctx.m_off == 0:
-            T = buf
-        else:
-            T = torch.zeros((E, m_cols), dtype=gE.dtype, device=gE.device) if ctx.m_off else \
-                torch.empty((E, H), dtype=gE.dtype, device=gE.device)
-        # d(coef * P) = coef ⊙ gE is never materialised: both of its consumers (dX_e and dW_sd) take `coef` as a
-        # per-row scale of their streamed operand (fp32 product rounded exactly like the reference's `coef * gE`)
-        edge_backward(plan, ctx.norm_flat, gN_full, gE, want_CG=False, t_rev_col_offset=ctx.m_off, T=T)
-        del buf2
-        del gN_full
+        w_sd = src_w - dst_w
+        Din = in_w.shape[0]
+        # Gradient of the node aggregation w.r.t. the edge side.  On the tensor-core path nothing edge-sized is
+        # materialised for it: dX_e receives  sgn*norm*(gN W_n^T)[dst]  from node-sized tables inside the GEMM epilogue
+        # and dW_in / dW_out come from aggregate-first sums (segment reduce of X_e by destination, then a node-sized
+        # reduction).  Otherwise T = sgn*norm*gN[dst] is written out and fed to plain GEMMs.
+        gather = (need_xe or need_w) and _use_tc(gE, w_sd) and Din in (64, 128)
+        T = None
+        if not gather:
+            m_cols = H + ctx.m_off
+            if buf is not None and ctx.m_off == 0:
+                T = buf
+            else:
+                T = torch.zeros((E, m_cols), dtype=gE.dtype, device=gE.device) if ctx.m_off else \
+                    torch.empty((E, H), dtype=gE.dtype, device=gE.device)
+            edge_backward(plan, ctx.norm_flat, gN_full, gE, want_CG=False, t_rev_col_offset=ctx.m_off, T=T)
+        del buf, buf2
 
         # ---- dense backward --------------------------------------------------------------------------------
-        w_sd = src_w - dst_w
         dX_v = dX_e = None
         if need_xv:
             if part is None:
@@ -258,16 +265,24 @@ class _FusedDMPLayer(torch.autograd.Function):
                 del partial
         if need_xe:
             dX_e = _rowmm(gE, eloop_w)
-            _rowmm(gE, w_sd, out=dX_e, accumulate=True, row_scale=plan.coef)
-            if plan.rev_layout == "none":
-                _rowmm(T, in_w, out=dX_e, accumulate=True)
-            elif plan.rev_layout == "halves":
-                h = plan.rev_split
-                _rowmm(T[:h], in_w, out=dX_e[:h], accumulate=True)
-                _rowmm(T[h:], out_w, out=dX_e[h:], accumulate=True)
+            if gather:
+                # coef ⊙ gE is a per-row scale of the streamed operand; the message gradient is an epilogue gather
+                tab_in = _rowmm(gN_full, in_w)
+                tab_out = _rowmm(gN_full, out_w) if plan.rev is not None else None
+                gemm_tf32x3_acc_gather(gE, w_sd, dX_e, dst32=plan.dst32, tab_fwd=tab_in, tab_rev=tab_out, rev=plan.rev,
+                                       norm=ctx.norm_flat, row_scale=plan.coef)
+                del tab_in, tab_out
             else:
-                _rowmm(T[:, :H], in_w, out=dX_e, accumulate=True)
-                _rowmm(T[:, H:], out_w, out=dX_e, accumulate=True)
+                _rowmm(gE, w_sd, out=dX_e, accumulate=True, row_scale=plan.coef)
+                if plan.rev_layout == "none":
+                    _rowmm(T, in_w, out=dX_e, accumulate=True)
+                elif plan.rev_layout == "halves":
+                    h = plan.rev_split
+                    _rowmm(T[:h], in_w, out=dX_e[:h], accumulate=True)
+                    _rowmm(T[h:], out_w, out=dX_e[h:], accumulate=True)
+                else:
+                    _rowmm(T[:, :H], in_w, out=dX_e, accumulate=True)
+                    _rowmm(T[:, H:], out_w, out=dX_e, accumulate=True)
         d_in = d_out = d_src = d_dst = d_nloop = d_eloop = d_nb = d_eb = None
         if need_w:
             d_nloop, _, d_nb = _tnmm(X_v, gN, colsum_g=True)
@@ -281,7 +296,18 @@ class _FusedDMPLayer(torch.autograd.Function):
             d_dst.sub_(d_sd)
             d_src = _tnmm(X_v_full, dQs)
             d_src.add_(d_sd)
-            if plan.rev_layout == "none":
+            if gather:
+                seg_ptr = plan.csc_indptr if part is None else plan.csc_indptr[part[0]:part[1] + 1]
+                a_in = segment_reduce(seg_ptr, plan.csc_eid, X_e, Din, w_perm=ctx.norm_perm,
+                                      mode=_lib.SEG_SIGN_BY_REV | _lib.SEG_ONLY_FWD, tag="segment_reduce.dWin_bwd")
+                d_in = _tnmm(a_in, gN)
+                if plan.rev is not None:
+                    a_out = segment_reduce(seg_ptr, plan.csc_eid, X_e, Din, w_perm=ctx.norm_perm,
+                                           mode=_lib.SEG_SIGN_BY_REV | _lib.SEG_ONLY_REV, tag="segment_reduce.dWout_bwd")
+                    d_out = _tnmm(a_out, gN)
+                else:
+                    d_out = torch.zeros_like(out_w)
+            elif plan.rev_layout == "none":
                 d_in = _tnmm(X_e, T)
                 d_out = torch.zeros_like(out_w)
             elif plan.rev_layout == "halves":

@@ -47,6 +47,8 @@ extern "C" {
 /* dmp_segment_reduce mode bits */
 #define DMP_SEG_SIGN_BY_REV 1 /* message sign: -1 on forward edges, +1 on reversed edges (dmpnn.py:113,121) */
 #define DMP_SEG_NEGATE_OUT 2  /* out = -(sum)  (used for dQ_s = -SB in backward)                         */
+#define DMP_SEG_ONLY_FWD 4    /* skip reversed edges (their rows are not even loaded)                     */
+#define DMP_SEG_ONLY_REV 8    /* skip forward edges                                                        */
 
 /* dmp_edge_update order */
 #define DMP_ORDER_SCM 0 /* ((eloop + add) + agg) + ebias   dmpnn.py:147-149  */
@@ -174,6 +176,14 @@ DMP_API int dmp_gate_residual_backward(const float* gout, int64_t ld_gout, const
 DMP_API int dmp_gemm_tf32x3(const float* A, int64_t lda, const float* row_scale, const float* Bt, int64_t ldb,
                             const float* bias, const float* aux, int64_t ld_aux, float* D, int64_t ldd,
                             int64_t M, int64_t N, int64_t K, int epilogue, float slope, void* stream);
+
+/* Backward of `fn.sum` folded into the edge-gradient projection (no [E,H] message-gradient tensor is materialised):
+ *   D[r,:] += (row_scale ⊙ A)[r,:] · Bt^T + sgn_r * norm_r * tab_{rev_r}[dst32[r], :]      sgn_r = rev[r] ? +1 : -1
+ * with tab_fwd = gN·W_in^T, tab_rev = gN·W_out^T (node-sized).  rev / norm / row_scale may be NULL. */
+DMP_API int dmp_gemm_tf32x3_acc_gather(const float* A, int64_t lda, const float* row_scale, const float* Bt,
+                                       int64_t ldb, float* D, int64_t ldd, int64_t M, int64_t N, int64_t K,
+                                       const int32_t* dst32, const uint8_t* rev, const float* norm,
+                                       const float* tab_fwd, const float* tab_rev, int64_t ld_tab, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Weight-gradient reduction on the tensor cores (3xTF32 split, fp32-level accuracy):

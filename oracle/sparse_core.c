@@ -27,6 +27,7 @@ void oracle_seg_reduce(const int32_t* indptr, const uint32_t* eid, const float* 
     for (int64_t h = 0; h < H; ++h) acc[h] = 0.0f;
     for (int32_t j = indptr[x]; j < indptr[x + 1]; ++j) {
       uint32_t r = eid[j] >> 31;
+      if (((mode & 4) && r) || ((mode & 8) && !r)) continue; /* ONLY_FWD / ONLY_REV */
       const float* row = V + (int64_t)(eid[j] & EID_MASK) * ldV + (r ? rev_off : 0);
       int neg = (mode & 1) && !r;
       for (int64_t h = 0; h < H; ++h) {

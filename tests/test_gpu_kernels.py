@@ -177,3 +177,24 @@ def test_full_size_properties_config5_slice():
     torch.testing.assert_close(out.double().sum(0), want, rtol=1e-6, atol=1e-2)
     out2 = F.segment_reduce(plan.csc_indptr, plan.csc_eid, M * 2, H, mode=_lib.SEG_SIGN_BY_REV)
     assert torch.equal(out2, out * 2)  # scaling by a power of two commutes with every rounding
+
+
+@pytest.mark.parametrize("H", [32, 128])
+def test_segment_reduce_flag_filters_bit_exact(H):
+    """ONLY_FWD / ONLY_REV (aggregate-first dW_in / dW_out in backward) against the C oracle."""
+    from dualmessagepassing_b200 import _lib, functional as F
+    s, d, r = make_graph(seed=99, n=300, e0=2500, rev="shuffled")
+    plan = _plan(s, d, 300, r)
+    cp = _cpu_plan(plan)
+    E = len(s)
+    g = torch.Generator().manual_seed(H)
+    X, norm = torch.randn(E, H, generator=g), torch.rand(E, generator=g)
+    w_cpu = norm[(cp["csc_eid"].long() & 0x7FFFFFFF)]
+    w_gpu = plan.norm_permuted(norm.cuda())[1]
+    for filt in (_lib.SEG_ONLY_FWD, _lib.SEG_ONLY_REV):
+        mode = _lib.SEG_SIGN_BY_REV | filt
+        want = sc.seg_reduce(cp["csc_indptr"], cp["csc_eid"], X, H, w_perm=w_cpu, mode=mode)
+        got = F.segment_reduce(plan.csc_indptr, plan.csc_eid, X.cuda(), H, w_perm=w_gpu, mode=mode)
+        assert torch.equal(got.cpu(), want)
+    both = sc.seg_reduce(cp["csc_indptr"], cp["csc_eid"], X, H, w_perm=w_cpu, mode=_lib.SEG_SIGN_BY_REV)
+    assert float(both.abs().sum()) > 0
