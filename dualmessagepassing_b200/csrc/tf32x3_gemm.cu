@@ -235,8 +235,11 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) tf32x3_gemm_kernel(const Gemm
           prefetch_l2_bulk(p.A + r0 * p.lda, (uint32_t)(((rows - 1) * p.lda + K) * 4));
         }
       };
+      // ncu (profiles/r1_ncu_summary_cfg5.md): with the bulk L2 prefetch on, DRAM reads were 1.8x the operand size
+      // (prefetched lines were fetched again by the cp.async that followed); off by default.
       constexpr int kL2Ahead = 4;
-      for (int t = 2; t <= kL2Ahead; ++t) l2_prefetch_tile(t);
+      constexpr bool kUseL2Prefetch = false;
+      if (kUseL2Prefetch) for (int t = 2; t <= kL2Ahead; ++t) l2_prefetch_tile(t);
 #pragma unroll
       for (int d = 0; d < kCopyDepth; ++d) {
         if (d < total_kb) issue(d);
@@ -244,7 +247,7 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) tf32x3_gemm_kernel(const Gemm
       }
       int stage = 0;
       for (int64_t it = 0; it < total_kb; ++it) {
-        if (it % kKBlocks == 0) l2_prefetch_tile(it / kKBlocks + kL2Ahead + 1);
+        if (kUseL2Prefetch && it % kKBlocks == 0) l2_prefetch_tile(it / kKBlocks + kL2Ahead + 1);
         cp_async_wait<kCopyDepth - 1>();                      // this thread's copies of k-block `it` have landed
         const uint32_t hi = sA + stage * L::kStageBytes;
         const uint32_t lo = hi + L::kABlockBytes;

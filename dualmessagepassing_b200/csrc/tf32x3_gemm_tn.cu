@@ -41,6 +41,7 @@ struct TnParams {
   int64_t E;
   uint32_t lbo, sbo, kadv;   // descriptor geometry (bytes); defaults set by the host wrapper
   uint32_t idesc_xor, ltype;
+  int l2_prefetch;
 };
 
 // kind::tf32, fp32 accumulate, A and B MN-major
@@ -166,7 +167,8 @@ __global__ void __launch_bounds__(kTnThreads, 1) tf32x3_gemm_tn_kernel(const TnP
       }
     };
     constexpr int kL2Ahead = 12;
-    for (int st = kTnPrefetch; st < kL2Ahead; ++st) l2_prefetch(st);
+    const bool use_l2_prefetch = p.l2_prefetch != 0;
+    if (use_l2_prefetch) for (int st = kTnPrefetch; st < kL2Ahead; ++st) l2_prefetch(st);
     int64_t st_load = 0;
 #pragma unroll
     for (int slot = 0; slot < kTnPrefetch; ++slot)
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(kTnThreads, 1) tf32x3_gemm_tn_kernel(const TnP
 #pragma unroll
       for (int slot = 0; slot < kTnPrefetch; ++slot) {
         if (st0 + slot < n_stages) {
-          l2_prefetch(st0 + slot + kL2Ahead);
+          if (use_l2_prefetch) l2_prefetch(st0 + slot + kL2Ahead);
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           const uint32_t x_hi = base + stage * L::kStageBytes, x_lo = x_hi + L::kXBytes;
           const uint32_t g_hi = x_lo + L::kXBytes, g_lo = g_hi + L::kGBytes;
@@ -415,6 +417,7 @@ extern "C" int dmp_gemm_tn_tf32x3(const float* X, int64_t ldx, const float* row_
   p.part_sg = colsum_g ? p.partial + grid * (M * N + M) : nullptr;
   // 4096 B between 32-feature blocks (LBO), 512 B between 4-edge atoms (SBO), 1024 B per MMA k-step (8 edges)
   p.lbo = kTnEdges * 128; p.sbo = 512; p.kadv = 1024; p.idesc_xor = 0; p.ltype = 1;
+  p.l2_prefetch = getenv("DMP_TN_L2PF") ? atoi(getenv("DMP_TN_L2PF")) : 1;
   if (const char* dbg = getenv("DMP_TN_DBG"))
     sscanf(dbg, "%u,%u,%u,%u,%u", &p.lbo, &p.sbo, &p.kadv, &p.idesc_xor, &p.ltype);
   cudaStream_t s = (cudaStream_t)stream;
