@@ -30,7 +30,7 @@ struct SegParams {
   int mode;
 };
 
-template <int VEC, int G, int ITER, int U>
+template <int VEC, int G, int ITER, int U, bool FILTER>
 __global__ void __launch_bounds__(kThreads) segment_reduce_kernel(const SegParams p) {
   constexpr int kGroups = kThreads / G;
   const int lane = threadIdx.x % G;
@@ -70,9 +70,11 @@ __global__ void __launch_bounds__(kThreads) segment_reduce_kernel(const SegParam
     Row<VEC> v[U][ITER];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const bool keep = (j + u < end) && !((filt & DMP_SEG_ONLY_FWD) && (ef[u] >> 31)) &&
-                        !((filt & DMP_SEG_ONLY_REV) && !(ef[u] >> 31));
-      if (!keep) ef[u] = 0xffffffffu;   // sentinel: (id mask, rev) can never both be all-ones for a real edge
+      bool keep = j + u < end;
+      if constexpr (FILTER) {
+        keep = keep && !((filt & DMP_SEG_ONLY_FWD) && (ef[u] >> 31)) && !((filt & DMP_SEG_ONLY_REV) && !(ef[u] >> 31));
+        if (!keep) ef[u] = 0xffffffffu;   // sentinel: (id mask, rev) can never both be all-ones for a real edge
+      }
       if (keep) {
         const uint32_t r = ef[u] >> 31;
         const float* row = p.V + (int64_t)(ef[u] & DMP_EID_MASK) * p.ldV + (r ? p.rev_off : 0);
@@ -83,7 +85,7 @@ __global__ void __launch_bounds__(kThreads) segment_reduce_kernel(const SegParam
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      if (j + u < end && ef[u] != 0xffffffffu) {
+      if (j + u < end && (!FILTER || ef[u] != 0xffffffffu)) {
         const bool neg = sign_by_rev && (ef[u] >> 31) == 0;
 #pragma unroll
         for (int it = 0; it < ITER; ++it) {
@@ -124,13 +126,15 @@ __global__ void __launch_bounds__(kThreads) segment_reduce_kernel(const SegParam
 
 template <int VEC, int G, int ITER, int U>
 static int launch(const SegParams& p, cudaStream_t stream) {
+  const bool filter = (p.mode & (DMP_SEG_ONLY_FWD | DMP_SEG_ONLY_REV)) != 0;
   constexpr int kGroups = kThreads / G;
   const int64_t blocks = (p.nseg + kGroups - 1) / kGroups;
   if (blocks > 0x7fffffffLL) {
     set_error("segment_reduce: too many segments (%lld)", (long long)p.nseg);
     return DMP_ERR_UNSUPPORTED;
   }
-  segment_reduce_kernel<VEC, G, ITER, U><<<(unsigned)blocks, kThreads, 0, stream>>>(p);
+  if (filter) segment_reduce_kernel<VEC, G, ITER, U, true><<<(unsigned)blocks, kThreads, 0, stream>>>(p);
+  else segment_reduce_kernel<VEC, G, ITER, U, false><<<(unsigned)blocks, kThreads, 0, stream>>>(p);
   return launch_status("segment_reduce_kernel");
 }
 

@@ -6,11 +6,12 @@
 //
 // The contraction index (the edge) is the SLOW index of both row-major operands, i.e. both are "MN-major" for
 // the MMA; tcgen05 kind::tf32 accepts that directly, so no transpose is staged:
-//   smem tile of 32 edges x 128 features = 4 column blocks (32 features = 128 B) x 32 edge rows; a block is
-//   four 8-row / 1024-byte 128B-swizzle atoms (SBO = 1024 B between 8-edge groups, LBO = 4096 B between
-//   feature blocks); the descriptor start advances by 1024 B per MMA k-step (8 edges).
-// Structure mirrors tf32x3_gemm.cu: 8 producer warps (coalesced 512-byte row loads -> row scale -> hi/lo split ->
-// swizzled smem), 1 MMA warp (12 tcgen05.mma per 32-edge stage), 8 flush warps.  Each CTA owns a contiguous range
+//   smem tile of 16 edges x 128 features = 4 column blocks (32 features = 128 B) x 16 edge rows; a block is
+//   four 4-row / 512-byte atoms of the SWIZZLE_128B_BASE32B layout (SBO = 512 B between 4-edge atoms, LBO = 2048 B
+//   between feature blocks); the descriptor start advances by 1024 B per MMA k-step (8 edges).
+// Structure mirrors tf32x3_gemm.cu: 8 producer warps (cp.async of whole 512-byte rows into the swizzled hi tile, then
+// lo = x - trunc_tf32(x), optional row scale and running column sums), 1 MMA warp (6 tcgen05.mma per 16-edge stage),
+// 8 flush warps.  Each CTA owns a contiguous range
 // of edges; to bound the length of any tensor-core accumulation chain the accumulator is double-buffered in TMEM
 // and FLUSHED every kFlushStages stages into an fp32 partial in global memory (round-to-nearest adds, L2-resident),
 // and a second kernel adds the per-CTA partials in a fixed order -> deterministic, no atomics.
@@ -21,15 +22,15 @@
 namespace dmp {
 namespace gemm {
 
-constexpr int kTnEdges = 32;            // edges per stage (4 MMA k-steps)
-constexpr int kTnStages = 3;
+constexpr int kTnEdges = 16;            // edges per stage (2 MMA k-steps): small stages -> 6 of them fit, and the
+constexpr int kTnStages = 6;            // asynchronous copies can run kTnCopyDepth stages (64 KB per SM) ahead
+constexpr int kTnCopyDepth = kTnStages - 2;
 constexpr int kTnProducerWarps = 8;
 constexpr int kTnProducerThreads = kTnProducerWarps * 32;
 constexpr int kTnFlushWarps = 8;
 constexpr int kTnMmaWarp = 8;
 constexpr int kTnThreads = (kTnFlushWarps + 1 + kTnProducerWarps) * 32;  // 544
-constexpr int kTnPrefetch = 2;          // stages of global loads in flight per producer thread
-constexpr int kFlushStages = 16;        // 512 edges per tensor-core accumulation chain
+constexpr int kFlushStages = 32;        // 512 edges per tensor-core accumulation chain
 
 struct TnParams {
   const float* X; int64_t ldx;
@@ -123,106 +124,81 @@ __global__ void __launch_bounds__(kTnThreads, 1) tf32x3_gemm_tn_kernel(const TnP
   if (warp > kTnMmaWarp) {
     // =========================== PRODUCERS ===========================
     const int pt = threadIdx.x - (kTnMmaWarp + 1) * 32;   // 0..255
-    // X tile: 32 edges x M/4 chunks; thread handles chunk ids pt + 256*i.  A warp covers whole 512-byte rows.
+    // X tile: 16 edges x M/4 chunks of 16 B; thread handles chunk ids pt + 256*i.  A warp covers whole rows.
     constexpr int kXChunks = kTnEdges * M / 4, kGChunks = kTnEdges * N / 4;
-    constexpr int kXPer = kXChunks / kTnProducerThreads, kGPer = kGChunks / kTnProducerThreads;   // 4 (or 2)
-    float4 bx[kTnPrefetch][kXPer], bg[kTnPrefetch][kGPer];
+    constexpr int kXPer = kXChunks / kTnProducerThreads, kGPer = kGChunks / kTnProducerThreads;   // 2 (or 1)
     // bias gradients for free: a thread always handles the same 4 columns (256 % (M/4) == 0), so it keeps running
     // column sums of everything it streams; rows past E are zero-filled and add nothing
     float4 sum_x = make_float4(0.f, 0.f, 0.f, 0.f), sum_g = sum_x;
-    auto load_stage = [&](int64_t st, float4 (&dx)[kXPer], float4 (&dg)[kGPer]) {
+    uint32_t offx[kXPer], offg[kGPer];
+#pragma unroll
+    for (int i = 0; i < kXPer; ++i) offx[i] = swz_mn((pt + kTnProducerThreads * i) / (M / 4), (pt + kTnProducerThreads * i) % (M / 4));
+#pragma unroll
+    for (int i = 0; i < kGPer; ++i) offg[i] = swz_mn((pt + kTnProducerThreads * i) / (N / 4), (pt + kTnProducerThreads * i) % (N / 4));
+    int istage = 0;
+    uint32_t iphase = 0;
+    auto issue = [&](int64_t st) {
+      mbar_wait(bar_empty + 8 * istage, iphase ^ 1);
       const int64_t e0 = (s_begin + st) * kTnEdges;
+      const uint32_t x_hi = base + istage * L::kStageBytes, g_hi = x_hi + 2 * L::kXBytes;
 #pragma unroll
       for (int i = 0; i < kXPer; ++i) {
         const int c = pt + kTnProducerThreads * i;
         const int64_t e = e0 + c / (M / 4);
-        if (e < p.E) {
-          const float* src = p.X + e * p.ldx + (c % (M / 4)) * 4;
-          asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                       : "=f"(dx[i].x), "=f"(dx[i].y), "=f"(dx[i].z), "=f"(dx[i].w) : "l"(src));
-        } else {
-          dx[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        const bool ok = e < p.E;
+        cp_async16(x_hi + offx[i], ok ? (const void*)(p.X + e * p.ldx + (c % (M / 4)) * 4) : (const void*)p.X, ok ? 16u : 0u);
       }
 #pragma unroll
       for (int i = 0; i < kGPer; ++i) {
         const int c = pt + kTnProducerThreads * i;
         const int64_t e = e0 + c / (N / 4);
-        if (e < p.E) {
-          const float* src = p.G + e * p.ldg + (c % (N / 4)) * 4;
-          asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                       : "=f"(dg[i].x), "=f"(dg[i].y), "=f"(dg[i].z), "=f"(dg[i].w) : "l"(src));
-        } else {
-          dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        const bool ok = e < p.E;
+        cp_async16(g_hi + offg[i], ok ? (const void*)(p.G + e * p.ldg + (c % (N / 4)) * 4) : (const void*)p.G, ok ? 16u : 0u);
       }
+      if (++istage == kTnStages) { istage = 0; iphase ^= 1; }
     };
-    // contiguous edge range -> bulk L2 prefetch a few stages ahead (one 512-byte row per thread and operand)
-    auto l2_prefetch = [&](int64_t st) {   // one thread per operand, one bulk prefetch per 32-edge stage
-      if (st < n_stages && (pt == 0 || pt == 32)) {
-        const int64_t e0 = (s_begin + st) * kTnEdges;
-        const int64_t rows = (p.E - e0) < kTnEdges ? (p.E - e0) : kTnEdges;
-        if (pt == 0) prefetch_l2_bulk(p.X + e0 * p.ldx, (uint32_t)(((rows - 1) * p.ldx + M) * 4));
-        else prefetch_l2_bulk(p.G + e0 * p.ldg, (uint32_t)(((rows - 1) * p.ldg + N) * 4));
-      }
-    };
-    constexpr int kL2Ahead = 12;
-    const bool use_l2_prefetch = p.l2_prefetch != 0;
-    if (use_l2_prefetch) for (int st = kTnPrefetch; st < kL2Ahead; ++st) l2_prefetch(st);
-    int64_t st_load = 0;
 #pragma unroll
-    for (int slot = 0; slot < kTnPrefetch; ++slot)
-      if (slot < n_stages) {
-        load_stage(slot, bx[slot], bg[slot]);
-        ++st_load;
-      }
+    for (int d = 0; d < kTnCopyDepth; ++d) {
+      if (d < n_stages) issue(d);
+      cp_async_commit();
+    }
     int stage = 0;
-    uint32_t phase = 0;
-    for (int64_t st0 = 0; st0 < n_stages; st0 += kTnPrefetch) {
+    for (int64_t st = 0; st < n_stages; ++st) {
+      cp_async_wait<kTnCopyDepth - 1>();                       // this thread's copies of stage `st` have landed
+      const uint32_t x_hi = base + stage * L::kStageBytes, x_lo = x_hi + L::kXBytes;
+      const uint32_t g_hi = x_lo + L::kXBytes, g_lo = g_hi + L::kGBytes;
 #pragma unroll
-      for (int slot = 0; slot < kTnPrefetch; ++slot) {
-        if (st0 + slot < n_stages) {
-          if (use_l2_prefetch) l2_prefetch(st0 + slot + kL2Ahead);
-          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-          const uint32_t x_hi = base + stage * L::kStageBytes, x_lo = x_hi + L::kXBytes;
-          const uint32_t g_hi = x_lo + L::kXBytes, g_lo = g_hi + L::kGBytes;
-#pragma unroll
-          for (int i = 0; i < kXPer; ++i) {
-            const int c = pt + kTnProducerThreads * i;
-            float4 v = bx[slot][i];
-            if constexpr (SX) {
-              sum_x.x = __fadd_rn(sum_x.x, v.x); sum_x.y = __fadd_rn(sum_x.y, v.y);
-              sum_x.z = __fadd_rn(sum_x.z, v.z); sum_x.w = __fadd_rn(sum_x.w, v.w);
-            }
-            if (p.row_scale != nullptr) {
-              const int64_t e = (s_begin + st0 + slot) * kTnEdges + c / (M / 4);
-              const float s = e < p.E ? __ldg(p.row_scale + e) : 1.0f;
-              v.x = __fmul_rn(s, v.x); v.y = __fmul_rn(s, v.y); v.z = __fmul_rn(s, v.z); v.w = __fmul_rn(s, v.w);
-            }
-            const uint32_t off = swz_mn(c / (M / 4), c % (M / 4));
-            split_store(x_hi + off, x_lo + off, v);
-          }
-#pragma unroll
-          for (int i = 0; i < kGPer; ++i) {
-            const int c = pt + kTnProducerThreads * i;
-            const uint32_t off = swz_mn(c / (N / 4), c % (N / 4));
-            const float4 gv = bg[slot][i];
-            if constexpr (SG) {
-              sum_g.x = __fadd_rn(sum_g.x, gv.x); sum_g.y = __fadd_rn(sum_g.y, gv.y);
-              sum_g.z = __fadd_rn(sum_g.z, gv.z); sum_g.w = __fadd_rn(sum_g.w, gv.w);
-            }
-            split_store(g_hi + off, g_lo + off, gv);
-          }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_full + 8 * stage);
-          if (st_load < n_stages) {
-            load_stage(st_load, bx[slot], bg[slot]);
-            ++st_load;
-          }
-          if (++stage == kTnStages) { stage = 0; phase ^= 1; }
+      for (int i = 0; i < kXPer; ++i) {
+        float4 v = lds128(x_hi + offx[i]);
+        if constexpr (SX) {
+          sum_x.x = __fadd_rn(sum_x.x, v.x); sum_x.y = __fadd_rn(sum_x.y, v.y);
+          sum_x.z = __fadd_rn(sum_x.z, v.z); sum_x.w = __fadd_rn(sum_x.w, v.w);
         }
+        if (p.row_scale != nullptr) {
+          const int64_t e = (s_begin + st) * kTnEdges + (pt + kTnProducerThreads * i) / (M / 4);
+          const float sc = e < p.E ? __ldg(p.row_scale + e) : 1.0f;
+          v.x = __fmul_rn(sc, v.x); v.y = __fmul_rn(sc, v.y); v.z = __fmul_rn(sc, v.z); v.w = __fmul_rn(sc, v.w);
+          sts128(x_hi + offx[i], v);
+        }
+        sts128(x_lo + offx[i], make_float4(tf32_trunc_residual(v.x), tf32_trunc_residual(v.y),
+                                           tf32_trunc_residual(v.z), tf32_trunc_residual(v.w)));
       }
+#pragma unroll
+      for (int i = 0; i < kGPer; ++i) {
+        const float4 v = lds128(g_hi + offg[i]);
+        if constexpr (SG) {
+          sum_g.x = __fadd_rn(sum_g.x, v.x); sum_g.y = __fadd_rn(sum_g.y, v.y);
+          sum_g.z = __fadd_rn(sum_g.z, v.z); sum_g.w = __fadd_rn(sum_g.w, v.w);
+        }
+        sts128(g_lo + offg[i], make_float4(tf32_trunc_residual(v.x), tf32_trunc_residual(v.y),
+                                           tf32_trunc_residual(v.z), tf32_trunc_residual(v.w)));
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_full + 8 * stage);
+      if (++stage == kTnStages) stage = 0;
+      if (st + kTnCopyDepth < n_stages) issue(st + kTnCopyDepth);
+      cp_async_commit();
     }
     if constexpr (SX || SG) {
       // threads with equal (pt % chunks-per-row) own the same columns: with 32 chunks per row that is one lane of each
@@ -417,7 +393,7 @@ extern "C" int dmp_gemm_tn_tf32x3(const float* X, int64_t ldx, const float* row_
   p.part_sg = colsum_g ? p.partial + grid * (M * N + M) : nullptr;
   // 4096 B between 32-feature blocks (LBO), 512 B between 4-edge atoms (SBO), 1024 B per MMA k-step (8 edges)
   p.lbo = kTnEdges * 128; p.sbo = 512; p.kadv = 1024; p.idesc_xor = 0; p.ltype = 1;
-  p.l2_prefetch = getenv("DMP_TN_L2PF") ? atoi(getenv("DMP_TN_L2PF")) : 1;
+  p.l2_prefetch = 0;
   if (const char* dbg = getenv("DMP_TN_DBG"))
     sscanf(dbg, "%u,%u,%u,%u,%u", &p.lbo, &p.sbo, &p.kadv, &p.idesc_xor, &p.ltype);
   cudaStream_t s = (cudaStream_t)stream;
