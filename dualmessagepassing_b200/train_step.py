@@ -136,7 +136,10 @@ class SubgraphCountingModel(nn.Module):
         indptr[1:] = torch.cumsum(n, 0)
         return _SegSum.apply(x, indptr, g.ndata["graph_id"])
 
-    def forward(self, pattern, graph):
+    def forward(self, pattern, graph, union=None):
+        """`union` (optional, from `union_graph(pattern, graph)`): run the SHARED layers once on the disjoint union of
+        the pattern batch and the graph batch instead of twice (share_rep_net, dmpnn.py:187-188) -- same arithmetic
+        per node/edge (the pattern side simply has gate 1), half the kernel launches."""
         bsz = pattern.batch_num_nodes().numel()
         # ScalarFilter-style gate (filter.py:6-16, basemodel.py:1394-1423): a graph node/edge passes if its
         # label occurs in the paired pattern
@@ -145,8 +148,14 @@ class SubgraphCountingModel(nn.Module):
         v_gate = pres_v[graph.ndata["graph_id"], graph.ndata[NODELABEL]]
         p_v, p_e = self._embed(pattern)
         g_v, g_e = self._embed(graph)
-        p_v, p_e = self.rep.get_pattern_rep(pattern, p_v, p_e)
-        g_v, g_e = self.rep.get_graph_rep(graph, g_v, g_e, v_gate=v_gate)
+        if union is None:
+            p_v, p_e = self.rep.get_pattern_rep(pattern, p_v, p_e)
+            g_v, g_e = self.rep.get_graph_rep(graph, g_v, g_e, v_gate=v_gate)
+        else:
+            np_, ne_ = p_v.shape[0], p_e.shape[0]
+            gate = torch.cat([torch.ones(np_, device=v_gate.device), v_gate])
+            u_v, u_e = self.rep.get_graph_rep(union, torch.cat([p_v, g_v]), torch.cat([p_e, g_e]), v_gate=gate)
+            p_v, g_v = u_v[:np_], u_v[np_:]
         p = self._pool(self.p_fc(p_v), pattern)
         g = self._pool(self.g_fc(g_v), graph)
         pl = pattern.batch_num_nodes().float().view(-1, 1)
@@ -154,6 +163,18 @@ class SubgraphCountingModel(nn.Module):
         extra = [pl, gl, 1.0 / pl, 1.0 / gl]
         y = self.act(self.pred_fc1(torch.cat([p, g, g - p, g * p] + extra, dim=1)))
         return self.pred_fc2(torch.cat([y] + extra, dim=1)).view(-1)
+
+
+def union_graph(pattern, graph):
+    """Disjoint union [pattern batch | graph batch] for the shared representation layers (one plan, one call)."""
+    np_ = pattern.number_of_nodes()
+    ps, pd = pattern.all_edges()
+    gs, gd = graph.all_edges()
+    u = DMPGraph(torch.cat([ps, gs + np_]), torch.cat([pd, gd + np_]), np_ + graph.number_of_nodes())
+    u.edata[REVFLAG] = torch.cat([pattern.edata[REVFLAG], graph.edata[REVFLAG]])
+    u.rev_layout_hint = "general"
+    u.validate_plan = False
+    return u
 
 
 class _SegSum(torch.autograd.Function):
@@ -169,10 +190,10 @@ class _SegSum(torch.autograd.Function):
         return g[row_segment], None, None
 
 
-def train_step(model, optimizer, pattern, graph, target, *, world=1, clip=10.0):
+def train_step(model, optimizer, pattern, graph, target, *, world=1, clip=10.0, fuse_batches=True):
     """forward -> MSE -> backward -> (gradient all-reduce) -> clip -> optimizer.  Returns the loss tensor (device)."""
     optimizer.zero_grad(set_to_none=True)
-    pred = model(pattern, graph)
+    pred = model(pattern, graph, union=union_graph(pattern, graph) if fuse_batches else None)
     loss = torch.mean((pred - target) ** 2)
     loss.backward()
     if world > 1:

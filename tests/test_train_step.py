@@ -38,3 +38,17 @@ def test_train_step_runs_and_learns():
     losses = [float(ts.train_step(model, opt, p, g, y)) for _ in range(30)]
     assert nb > 0 and all(np.isfinite(losses))
     assert losses[-1] < 0.7 * losses[0], losses
+
+
+@pytest.mark.gpu
+def test_union_of_pattern_and_graph_batches_equals_separate_calls():
+    """Shared layers on the disjoint union == the two separate calls (same per-row arithmetic; fp32 tolerance because
+    the dense projections see different row counts)."""
+    from dualmessagepassing_b200 import train_step as ts
+    ds = ts.SyntheticPairDataset("cfg3", num=32, seed=5)
+    torch.manual_seed(1)
+    model = ts.SubgraphCountingModel(128, 7, 4).cuda()
+    p, g, y, _ = ts.to_device(ts.collate(ds, np.arange(32)), torch.device("cuda"))
+    a = model(p, g)
+    b = model(p, g, union=ts.union_graph(p, g))
+    torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-4)
