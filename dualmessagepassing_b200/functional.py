@@ -223,7 +223,10 @@ def gemm_tf32x3(A, Wt, *, row_scale=None, bias=None, act="none", slope=0.0, aux=
         bias = bias.contiguous()
     _lib.call("dmp_gemm_tf32x3", A.device, _lib.ptr(A), lda, _lib.ptr(row_scale), _lib.ptr(Wt), ldb,
               _lib.ptr(bias), _lib.ptr(aux if mul_act_grad else None), ld_aux, _lib.ptr(out), ldd, M, N, K, epi,
-              float(slope), _stream(A), tag="gemm_tf32x3",
+              float(slope), _stream(A),
+              tag="gemm_tf32x3." + ("acc" if accumulate else "grad" if mul_act_grad else
+                                    "bias_act" if (bias is not None or act != "none") else "store") +
+                  ("_scaled" if row_scale is not None else ""),
               nbytes=4 * (M * K + M * N * (2 if accumulate else 1) + (M * N if mul_act_grad else 0) + N * K))
     return out
 
@@ -284,6 +287,6 @@ def gemm_tf32x3_acc_gather(A, Wt, out, *, dst32, tab_fwd, tab_rev=None, rev=None
         row_scale = row_scale.reshape(-1).contiguous()
     _lib.call("dmp_gemm_tf32x3_acc_gather", A.device, _lib.ptr(A), lda, _lib.ptr(row_scale), _lib.ptr(Wt), ldb,
               _lib.ptr(out), ldd, M, N, K, _lib.ptr(dst32), _lib.ptr(rev), _lib.ptr(norm), _lib.ptr(tab_fwd),
-              _lib.ptr(tab_rev), ld_tab, _stream(A), tag="gemm_tf32x3",
+              _lib.ptr(tab_rev), ld_tab, _stream(A), tag="gemm_tf32x3.acc_gather",
               nbytes=4 * (M * K + 3 * M * N + N * K) + 9 * M)
     return out
