@@ -427,6 +427,102 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) tf32x3_gemm_kernel(const Gemm
     uint32_t acc_phase = 0;
     int dbg_tile = 0;
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      if constexpr (N == 128 && MODE == kModeAccGather) {
+        // Gather epilogue, register-lean and latency-aware: 16 rows at a time; the operands that do not depend on
+        // the accumulator (previous D, row metadata, gathered table rows) are requested BEFORE waiting for the MMAs
+        // of this tile, so their DRAM latency hides behind the tensor-core work.
+        const int quad = warp & 3, half = warp >> 2;
+        const int f = quad * 32 + lane;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kTileM + half * 64);
+#pragma unroll 1
+        for (int sub = 0; sub < 4; ++sub) {
+          const int64_t r0 = tile * kTileM + half * 64 + sub * 16;
+          const int nvalid = (int)((p.M - r0) < 16 ? (p.M - r0) : 16);     // warp-uniform, may be <= 0
+          float* dst = p.D + r0 * p.ldd + f;
+          float old[16], g[16];
+          int d_l = 0, rv_l = 0;
+          float w_l = 1.0f;
+          if (lane < nvalid) {
+            d_l = __ldg(p.g_dst + r0 + lane);
+            if (p.g_rev != nullptr) rv_l = (int)__ldg(p.g_rev + r0 + lane);
+            if (p.g_norm != nullptr) w_l = __ldg(p.g_norm + r0 + lane);
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int d = __shfl_sync(0xffffffffu, d_l, j);
+            const int rv = __shfl_sync(0xffffffffu, rv_l, j);
+            if (j < nvalid) {
+              old[j] = dst[j * p.ldd];
+              g[j] = __ldg((rv ? p.g_tab1 : p.g_tab0) + (int64_t)d * p.ld_tab + f);
+            }
+          }
+          if (sub == 0) {
+            MBAR_WAIT(bar_acc_full + 8 * acc, acc_phase);
+            tc_fence_after();
+          }
+          float v[16];
+          tmem_ld16(t_lane + sub * 16, v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (j < nvalid) {
+              const int rv = __shfl_sync(0xffffffffu, rv_l, j);
+              float x = g[j];
+              if (p.g_norm != nullptr) x = __fmul_rn(x, __shfl_sync(0xffffffffu, w_l, j));
+              dst[j * p.ldd] = __fadd_rn(__fadd_rn(old[j], v[j]), rv ? x : -x);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_acc_empty + 8 * acc);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        ++dbg_tile;
+        continue;
+      }
+      if constexpr (N == 128 && (kNeedAux || MODE == kModeAccumulate)) {
+        // Epilogues with a streamed operand (previous D for accumulate, activation output for act'): one 32-row chunk
+        // at a time (64 live registers instead of 96: no spills), the operand of the first chunk is requested BEFORE
+        // waiting for this tile's MMAs so that its DRAM latency hides behind the tensor-core work.
+        const int quad = warp & 3, half = warp >> 2;
+        const int f = quad * 32 + lane;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kTileM + half * 64);
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          const int64_t r0 = tile * kTileM + half * 64 + c * 32;
+          const int nvalid = (int)((p.M - r0) < 32 ? (p.M - r0) : 32);     // warp-uniform, may be <= 0
+          float* dst = p.D + r0 * p.ldd + f;
+          const float* src = kNeedAux ? p.aux + r0 * p.ld_aux + f : dst;
+          const int64_t lds = kNeedAux ? p.ld_aux : p.ldd;
+          float t[32];
+          if (nvalid == 32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) t[j] = src[j * lds];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) t[j] = j < nvalid ? src[j * lds] : 0.0f;
+          }
+          if (c == 0) {
+            MBAR_WAIT(bar_acc_full + 8 * acc, acc_phase);
+            tc_fence_after();
+          }
+          float v[32];
+          tmem_ld32(t_lane + c * 32, v);
+          if (nvalid == 32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dst[j * p.ldd] = epilogue_op<MODE>(v[j], 0.0f, t[j], t[j], p.slope, act);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nvalid) dst[j * p.ldd] = epilogue_op<MODE>(v[j], 0.0f, t[j], t[j], p.slope, act);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_acc_empty + 8 * acc);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        ++dbg_tile;
+        continue;
+      }
       MBAR_WAIT(bar_acc_full + 8 * acc, acc_phase);
       if (dbg_ts && threadIdx.x == 0 && dbg_tile < 256) dbg_ts[1024 + 2 * dbg_tile] = clock64();
       tc_fence_after();
