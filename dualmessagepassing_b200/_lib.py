@@ -37,7 +37,7 @@ SIGNATURES = {
     "dmp_segment_reduce": [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _i32, _vp],
     "dmp_edge_update": [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _i64,
                         _i64, _i64, _i32, _vp],
-    "dmp_edge_backward": [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _i64, _vp],
+    "dmp_edge_backward": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _i64, _vp],
     "dmp_gate_residual": [_vp, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i32, _f32, _vp],
     "dmp_gate_residual_backward": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _i32, _f32, _vp],
     "dmp_gemm_tf32x3_acc_gather": [_vp, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp,

@@ -96,7 +96,7 @@ struct EdgeBwdParams {
   const uint8_t* rev;
   const float* norm;
   const float* coef;
-  const float* gN; int64_t ld_gN;
+  const float* gN; const float* gN_rev; int64_t ld_gN;
   const float* gE; int64_t ld_gE;
   float* T; int64_t ldT; int64_t T_rev_off;
   float* CG; int64_t ldCG;
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(kThreads) edge_backward_kernel(const EdgeBwdPa
       if (p.rev != nullptr) neg = __ldg(p.rev + e) == 0;
       t_off = neg ? 0 : p.T_rev_off;
       if (p.norm != nullptr) w = __ldg(p.norm + e);
-      const float* row = p.gN + (int64_t)d * p.ld_gN;
+      const float* row = (neg ? p.gN : p.gN_rev) + (int64_t)d * p.ld_gN;
 #pragma unroll
       for (int it = 0; it < ITER; ++it)
         if (ok[it]) g[it] = ld_row<VEC>(row + col[it]);
@@ -291,7 +291,7 @@ extern "C" int dmp_edge_update(const int32_t* a32, const int32_t* b32, const flo
 }
 
 extern "C" int dmp_edge_backward(const int32_t* dst32, const uint8_t* rev, const float* norm,
-                                 const float* coef, const float* gN, int64_t ld_gN, const float* gE,
+                                 const float* coef, const float* gN, const float* gN_rev, int64_t ld_gN, const float* gE,
                                  int64_t ld_gE, float* T, int64_t ldT, int64_t T_rev_col_offset, float* CG,
                                  int64_t ldCG, int64_t num_edges, int64_t H, void* stream) {
   using namespace dmp;
@@ -308,7 +308,7 @@ extern "C" int dmp_edge_backward(const int32_t* dst32, const uint8_t* rev, const
   for (int64_t c0 = 0; c0 < H; c0 += chunk) {
     EdgeBwdParams p;
     p.dst32 = dst32; p.rev = rev; p.norm = norm; p.coef = coef;
-    p.gN = gN ? gN + c0 : nullptr; p.ld_gN = ld_gN;
+    p.gN = gN ? gN + c0 : nullptr; p.gN_rev = gN_rev ? gN_rev + c0 : p.gN; p.ld_gN = ld_gN;
     p.gE = gE ? gE + c0 : nullptr; p.ld_gE = ld_gE;
     p.T = T ? T + c0 : nullptr; p.ldT = ldT; p.T_rev_off = T_rev_col_offset;
     p.CG = CG ? CG + c0 : nullptr; p.ldCG = ldCG;

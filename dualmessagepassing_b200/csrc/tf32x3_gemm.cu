@@ -214,9 +214,13 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) tf32x3_gemm_kernel(const Gemm
       for (int i = 0; i < 4; ++i) offs[i] = swz(row0 + 32 * i, c16);
       int istage = 0;
       uint32_t iphase = 0;
+      // per-row scales of the tile (same 4 rows for all k-blocks): fetched when the tile's first k-block is ISSUED
+      // (kCopyDepth stages ahead of its use), double-buffered by tile parity so the fetch latency is never exposed
+      float sc_a[4] = {1.f, 1.f, 1.f, 1.f}, sc_b[4] = {1.f, 1.f, 1.f, 1.f};
       auto issue = [&](int64_t it) {
         MBAR_WAIT(bar_empty + 8 * istage, iphase ^ 1);
-        const int64_t tile = (int64_t)blockIdx.x + (it / kKBlocks) * gridDim.x;
+        const int64_t tl = it / kKBlocks;
+        const int64_t tile = (int64_t)blockIdx.x + tl * gridDim.x;
         const int kb = (int)(it % kKBlocks);
         const uint32_t hi = sA + istage * L::kStageBytes;
 #pragma unroll
@@ -224,6 +228,10 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) tf32x3_gemm_kernel(const Gemm
           const int64_t r = tile * kTileM + row0 + 32 * i;
           const bool ok = r < p.M;
           cp_async16(hi + offs[i], ok ? (const void*)(p.A + r * p.lda + kb * kKB + c16 * 4) : (const void*)p.A, ok ? 16u : 0u);
+          if (kb == 0 && p.row_scale != nullptr) {
+            const float v = ok ? __ldg(p.row_scale + r) : 1.0f;
+            if (tl & 1) sc_b[i] = v; else sc_a[i] = v;
+          }
         }
         if (++istage == kStages) { istage = 0; iphase ^= 1; }
       };
@@ -252,11 +260,10 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) tf32x3_gemm_kernel(const Gemm
         const uint32_t hi = sA + stage * L::kStageBytes;
         const uint32_t lo = hi + L::kABlockBytes;
         if (p.row_scale != nullptr) {
-          const int64_t tile = (int64_t)blockIdx.x + (it / kKBlocks) * gridDim.x;
+          const bool odd = ((it / kKBlocks) & 1) != 0;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const int64_t r = tile * kTileM + row0 + 32 * i;
-            const float sc = r < p.M ? __ldg(p.row_scale + r) : 1.0f;
+            const float sc = odd ? sc_b[i] : sc_a[i];
             float4 v = lds128(hi + offs[i]);
             v.x = __fmul_rn(sc, v.x); v.y = __fmul_rn(sc, v.y); v.z = __fmul_rn(sc, v.z); v.w = __fmul_rn(sc, v.w);
             sts128(hi + offs[i], v);
@@ -434,6 +441,22 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) tf32x3_gemm_kernel(const Gemm
         const int quad = warp & 3, half = warp >> 2;
         const int f = quad * 32 + lane;
         const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kTileM + half * 64);
+        {
+          // The epilogue's own loads keep only ~32 KB per SM in flight (register bound), too little for random
+          // 128-byte table rows straight from DRAM.  So pull the NEXT tile's operands towards L2 now: lane j handles
+          // row j of this warp's 64-row half, each lane prefetches the one line its warp will read.
+          const int64_t nt = tile + gridDim.x;
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int64_t r = nt * kTileM + half * 64 + hh * 32 + lane;
+            if (nt < num_tiles && r < p.M) {
+              const int d = __ldg(p.g_dst + r);
+              const int rv = p.g_rev != nullptr ? (int)__ldg(p.g_rev + r) : 0;
+              asm volatile("prefetch.global.L2 [%0];" ::"l"((rv ? p.g_tab1 : p.g_tab0) + (int64_t)d * p.ld_tab + quad * 32));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.D + r * p.ldd + quad * 32));
+            }
+          }
+        }
 #pragma unroll 1
         for (int sub = 0; sub < 4; ++sub) {
           const int64_t r0 = tile * kTileM + half * 64 + sub * 16;

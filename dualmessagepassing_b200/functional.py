@@ -63,13 +63,18 @@ def edge_update(plan, S, P, Qd, Qs, ebias, order, out=None, edge_agg=None):
     return out
 
 
-def edge_backward(plan, norm_flat, gN, gE, *, want_T=True, want_CG=True, t_rev_col_offset=0, T=None, CG=None):
+def edge_backward(plan, norm_flat, gN, gE, *, want_T=True, want_CG=True, t_rev_col_offset=0, T=None, CG=None,
+                  gN_rev=None):
     """Raw call of dmp_edge_backward: T = sgn*gN[dst]*norm (optionally into the rev half), CG = coef*gE."""
     H = gN.shape[1] if gN is not None else gE.shape[1]
     dev = gN.device if gN is not None else gE.device
     ld_gN = ld_gE = ldT = ldCG = 0
     if want_T:
         gN, ld_gN = _lib.row_major(gN)
+        if gN_rev is not None:
+            gN_rev, ld2 = _lib.row_major(gN_rev)
+            if ld2 != ld_gN:
+                raise ValueError("gN and gN_rev must share a leading dimension")
         if T is None:
             if t_rev_col_offset:
                 T = torch.zeros((plan.E, t_rev_col_offset + H), dtype=torch.float32, device=dev)
@@ -83,7 +88,8 @@ def edge_backward(plan, norm_flat, gN, gE, *, want_T=True, want_CG=True, t_rev_c
         _, ldCG = _lib.row_major(CG)
     _lib.call("dmp_edge_backward", dev,
               _lib.ptr(plan.dst32), _lib.ptr(plan.rev), _lib.ptr(norm_flat), _lib.ptr(plan.coef),
-              _lib.ptr(gN if want_T else None), ld_gN, _lib.ptr(gE if want_CG else None), ld_gE,
+              _lib.ptr(gN if want_T else None), _lib.ptr(gN_rev if want_T else None), ld_gN,
+              _lib.ptr(gE if want_CG else None), ld_gE,
               _lib.ptr(T if want_T else None), ldT, t_rev_col_offset, _lib.ptr(CG if want_CG else None), ldCG,
               plan.E, H, _lib.stream_ptr(dev), tag="edge_backward")
     return (T if want_T else None), (CG if want_CG else None)

@@ -264,15 +264,19 @@ class _FusedDMPLayer(torch.autograd.Function):
                 _rowmm(gN, nloop_w, out=dX_v, accumulate=True)
                 del partial
         if need_xe:
-            dX_e = _rowmm(gE, eloop_w)
             if gather:
-                # coef ⊙ gE is a per-row scale of the streamed operand; the message gradient is an epilogue gather
+                # 1. dX_e <- sgn*norm*(gN W_n^T)[dst]: streaming gather from node-sized tables (high-occupancy kernel:
+                #    a GEMM epilogue cannot keep enough random 128-byte loads in flight, measured 37 ms vs 7 ms here)
+                # 2./3. both projections accumulate onto it; coef ⊙ gE is a per-row scale of the streamed operand
                 tab_in = _rowmm(gN_full, in_w)
                 tab_out = _rowmm(gN_full, out_w) if plan.rev is not None else None
-                gemm_tf32x3_acc_gather(gE, w_sd, dX_e, dst32=plan.dst32, tab_fwd=tab_in, tab_rev=tab_out, rev=plan.rev,
-                                       norm=ctx.norm_flat, row_scale=plan.coef)
+                dX_e = torch.empty((E, Din), dtype=gE.dtype, device=gE.device)
+                edge_backward(plan, ctx.norm_flat, tab_in, None, want_CG=False, T=dX_e, gN_rev=tab_out)
                 del tab_in, tab_out
+                _rowmm(gE, eloop_w, out=dX_e, accumulate=True)
+                _rowmm(gE, w_sd, out=dX_e, accumulate=True, row_scale=plan.coef)
             else:
+                dX_e = _rowmm(gE, eloop_w)
                 _rowmm(gE, w_sd, out=dX_e, accumulate=True, row_scale=plan.coef)
                 if plan.rev_layout == "none":
                     _rowmm(T, in_w, out=dX_e, accumulate=True)

@@ -140,9 +140,12 @@ DMP_API int dmp_edge_update(const int32_t* a32, const int32_t* b32, const float*
  * off_e = rev[e] ? T_rev_col_offset : 0 (mirror of dmp_segment_reduce's rev_col_offset: with the
  * two-branch [E,2H] message buffer the gradient lands in the half the edge's branch read from).
  * rev may be NULL (all forward), norm may be NULL.  T may be NULL to produce CG only.
+ * gN_rev (may be NULL = gN): table gathered for REVERSED edges.  With gN = dL/dnode_pre it is the plain
+ * gSpMM backward; with gN = gN·W_in^T and gN_rev = gN·W_out^T (node-sized tables) T is directly the
+ * contribution of the node aggregation to dL/dX_e, which the dense backward then accumulates onto.
  */
 DMP_API int dmp_edge_backward(const int32_t* dst32, const uint8_t* rev, const float* norm, const float* coef,
-                      const float* gN, int64_t ld_gN, const float* gE, int64_t ld_gE,
+                      const float* gN, const float* gN_rev, int64_t ld_gN, const float* gE, int64_t ld_gE,
                       float* T, int64_t ldT, int64_t T_rev_col_offset, float* CG, int64_t ldCG,
                       int64_t num_edges, int64_t H, void* stream);
 

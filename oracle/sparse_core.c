@@ -66,12 +66,12 @@ void oracle_edge_update(const int32_t* a32, const int32_t* b32, const float* coe
 }
 
 void oracle_edge_backward(const int32_t* dst32, const uint8_t* rev, const float* norm, const float* coef,
-                          const float* gN, int64_t ld_gN, const float* gE, int64_t ld_gE, float* T,
+                          const float* gN, const float* gN_rev, int64_t ld_gN, const float* gE, int64_t ld_gE, float* T,
                           int64_t ldT, int64_t T_rev_off, float* CG, int64_t ldCG, int64_t E, int64_t H) {
   for (int64_t e = 0; e < E; ++e) {
     if (T) {
-      const float* g = gN + (int64_t)dst32[e] * ld_gN;
       int neg = !(rev && rev[e]);
+      const float* g = ((neg || !gN_rev) ? gN : gN_rev) + (int64_t)dst32[e] * ld_gN;
       for (int64_t h = 0; h < H; ++h) {
         float x = g[h];
         if (norm) x = x * norm[e];

@@ -54,11 +54,11 @@ def edge_update(a32, b32, coef, S, P, Qd, Qs, ebias, order, want_agg=False):
     return (out, agg) if want_agg else out
 
 
-def edge_backward(dst32, rev, norm, coef, gN, gE, t_rev_off=0):
+def edge_backward(dst32, rev, norm, coef, gN, gE, t_rev_off=0, gN_rev=None):
     E, H = gE.shape
     T = torch.zeros((E, H + t_rev_off), dtype=torch.float32)
     CG = torch.empty((E, H), dtype=torch.float32)
-    lib().oracle_edge_backward(_p(dst32), _p(rev), _p(norm), _p(coef), _p(gN), _i64(gN.stride(0)), _p(gE),
+    lib().oracle_edge_backward(_p(dst32), _p(rev), _p(norm), _p(coef), _p(gN), _p(gN_rev), _i64(gN.stride(0)), _p(gE),
                                _i64(gE.stride(0)), _p(T), _i64(T.stride(0)), _i64(t_rev_off), _p(CG), _i64(H),
                                _i64(E), _i64(H))
     return T, CG

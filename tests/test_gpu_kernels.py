@@ -92,6 +92,11 @@ def test_edge_backward_bit_exact(n, e0, H):
             T, CG = F.edge_backward(plan, None if nm is None else nm.cuda(), gN.cuda(), gE.cuda(),
                                     t_rev_col_offset=off)
             assert torch.equal(T.cpu(), wT) and torch.equal(CG.cpu(), wCG)
+    # two gather tables (forward edges read gN, reversed edges gN_rev): the dX_e initialisation of the fused backward
+    gN2 = torch.randn(n, H, generator=g)
+    wT, _ = sc.edge_backward(cp["dst32"], r8, norm, cp["coef"], gN, gE, gN_rev=gN2)
+    T, _ = F.edge_backward(plan, norm.cuda(), gN.cuda(), None, want_CG=False, gN_rev=gN2.cuda())
+    assert torch.equal(T.cpu(), wT)
 
 
 def test_long_segment_hub_bit_exact_and_deterministic():
