@@ -2,19 +2,31 @@
 // on the tcgen05 tensor cores with fp32-level accuracy (3xTF32 split), M, N in {64, 128}, E = edges.
 //
 // Replaces the K = E long autograd reductions `X.t() @ G` of the DMPNN layer (dW_eloop, dW_src/dst, dW_in/out,
-// MLP dW1/dW2: 5 edge-sized reductions per layer, 145 of the 413 ms step at config 5 on cuBLAS sgemm).
+// MLP dW1/dW2: 4 edge-sized reductions per layer call, 145 of the 413 ms step at config 5 on cuBLAS sgemm).
 //
-// The contraction index (the edge) is the SLOW index of both row-major operands, i.e. both are "MN-major" for
-// the MMA; tcgen05 kind::tf32 accepts that directly, so no transpose is staged:
-//   smem tile of 16 edges x 128 features = 4 column blocks (32 features = 128 B) x 16 edge rows; a block is
-//   four 4-row / 512-byte atoms of the SWIZZLE_128B_BASE32B layout (SBO = 512 B between 4-edge atoms, LBO = 2048 B
-//   between feature blocks); the descriptor start advances by 1024 B per MMA k-step (8 edges).
-// Structure mirrors tf32x3_gemm.cu: 8 producer warps (cp.async of whole 512-byte rows into the swizzled hi tile, then
-// lo = x - trunc_tf32(x), optional row scale and running column sums), 1 MMA warp (6 tcgen05.mma per 16-edge stage),
-// 8 flush warps.  Each CTA owns a contiguous range
-// of edges; to bound the length of any tensor-core accumulation chain the accumulator is double-buffered in TMEM
-// and FLUSHED every kFlushStages stages into an fp32 partial in global memory (round-to-nearest adds, L2-resident),
-// and a second kernel adds the per-CTA partials in a fixed order -> deterministic, no atomics.
+// The contraction index (the edge) is the SLOW index of both row-major operands.
+//   * G is the B operand, read from shared memory "MN-major": a tile of 16 edges x 128 features = 4 column blocks
+//     (32 features = 128 B) x 16 edge rows; a block is four 4-row / 512-byte atoms of the SWIZZLE_128B_BASE32B layout
+//     (SBO = 512 B between 4-edge atoms, LBO = 2048 B between feature blocks); the descriptor start advances by
+//     1024 B per MMA k-step (8 edges).  cp.async lands whole rows directly in the swizzled hi tile (the tensor core
+//     ignores the low 13 mantissa bits, so the raw data IS the hi operand); the split writes lo = g - trunc_tf32(g)
+//     into a separate, shorter ring.
+//   * X^T is the A operand, read from TENSOR MEMORY (lane = feature, column = edge).  A warp copies its own 32-feature
+//     block of 16 rows into a private raw buffer, thread m then reads column m (conflict-free), applies the row scale,
+//     splits and writes 16 hi + 16 lo columns with tcgen05.st.  With both operands in shared memory the six MMAs of a
+//     stage read 48 KB of it and the kernel was bound by shared-memory bandwidth (MMA-only ablation 6.9 ms for 40 M
+//     edges, 0.55 of HBM peak overall); the TMEM form halves that and needs no second smem copy of X.
+// Warps: 0-7 X producers (TMEM lane quadrant = warp % 4; warps q and q+4 take even / odd stages, because the
+// lds -> tcgen05.st -> wait::st -> arrive chain of one stage is ~0.45 us of latency per warp), 8-11 flush, 12 MMA issuer
+// (6 tcgen05.mma per 16-edge stage), 13-16 G producers.  Ring sizing: a G hi slot is held from copy issue to MMA retirement, a lo slot only from split to
+// retirement: kTnCopyDepth stages of copies in flight (96 KB per SM) AND kTnLoStages of slack for the
+// split -> full barrier -> MMA -> commit -> done barrier round trip (measured ~1 us).  Holding the in-flight data in
+// registers instead does not work: ptxas puts every LDG of the loop on one scoreboard, so waiting for the oldest
+// load waits for all of them.
+// Each CTA owns a contiguous range of edges; to bound the length of any tensor-core accumulation chain the accumulator
+// is double-buffered in TMEM and FLUSHED every kFlushStages stages into an fp32 partial in global memory
+// (round-to-nearest adds, L2-resident), and a second kernel adds the per-CTA partials in a fixed order ->
+// deterministic, no atomics.
 #include <stdlib.h>
 
 #include "tc_common.cuh"
@@ -22,15 +34,22 @@
 namespace dmp {
 namespace gemm {
 
-constexpr int kTnEdges = 16;            // edges per stage (2 MMA k-steps): small stages -> 6 of them fit, and the
-constexpr int kTnStages = 6;            // asynchronous copies can run kTnCopyDepth stages (64 KB per SM) ahead
-constexpr int kTnCopyDepth = kTnStages - 2;
-constexpr int kTnProducerWarps = 8;
-constexpr int kTnProducerThreads = kTnProducerWarps * 32;
-constexpr int kTnFlushWarps = 8;
-constexpr int kTnMmaWarp = 8;
-constexpr int kTnThreads = (kTnFlushWarps + 1 + kTnProducerWarps) * 32;  // 544
-constexpr int kFlushStages = 32;        // 512 edges per tensor-core accumulation chain
+constexpr int kTnEdges = 32;            // edges per stage (4 MMA k-steps): every barrier round trip, tcgen05.st wait
+                                        // and commit is paid per stage, 16-edge stages spent 0.28 us on them alone
+constexpr int kTnCopyDepth = 3;         // stages of asynchronous copies in flight (96 KB per SM)
+constexpr int kTnLoStages = 2;          // ring of G residual tiles = slack between split and MMA retirement
+constexpr int kTnHiStages = kTnCopyDepth + kTnLoStages;   // ring of raw (= hi) G tiles
+constexpr int kTnXDepth = 2;                              // an X warp sees every second stage: copies in flight per warp
+constexpr int kTnXRaw = kTnXDepth + 1;                    // per-warp ring of raw 16 x 32 X blocks
+constexpr int kTnASlots = 4;            // TMEM ring of X^T: 32 hi + 32 lo columns per stage
+constexpr int kTnAColsPerSlot = 2 * kTnEdges;
+constexpr int kTnACol = 256;            // first TMEM column of that ring (accumulators: columns [0, 2N))
+constexpr int kTnXWarps = 8, kTnFlushWarps = 4, kTnGWarps = 4;
+constexpr int kTnMmaWarp = kTnXWarps + kTnFlushWarps;     // 12
+constexpr int kTnGThreads = kTnGWarps * 32;
+constexpr int kTnThreads = (kTnXWarps + kTnFlushWarps + 1 + kTnGWarps) * 32;  // 544
+constexpr int kFlushStages = 16;        // 512 edges per tensor-core accumulation chain
+constexpr int kTnTmemCols = 512;
 
 struct TnParams {
   const float* X; int64_t ldx;
@@ -42,26 +61,27 @@ struct TnParams {
   int64_t E;
   uint32_t lbo, sbo, kadv;   // descriptor geometry (bytes); defaults set by the host wrapper
   uint32_t idesc_xor, ltype;
-  int l2_prefetch;
+  int ablate;               // debug only (env DMP_TN_ABLATE): 1 no proxy fence, 2 no MMA, 4 no loads, 8 no split, 16 no flush
 };
 
-// kind::tf32, fp32 accumulate, A and B MN-major
+// kind::tf32, fp32 accumulate, A from tensor memory, B MN-major
 __host__ __device__ constexpr uint32_t make_idesc_mn(int m, int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) |
-         ((uint32_t)(m >> 4) << 24);
+  return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 template <int M, int N>
 struct TnSmem {
-  static constexpr int kXBytes = kTnEdges * 128 * 4;        // one of hi / lo; always 4 feature blocks: the MMA runs
-                                                            // with M = 128 (for M = 64 the upper two blocks stay zero)
-  static constexpr int kGBytes = kTnEdges * N * 4;
-  static constexpr int kStageBytes = 2 * kXBytes + 2 * kGBytes;
-  static constexpr int kSumBytes = 2 * kTnProducerWarps * 128 * 4;   // per-warp column-sum scratch (X and G)
-  static constexpr int kTotal = kTnStages * kStageBytes + 256 + kSumBytes + 1024;
+  static constexpr int kGBytes = kTnEdges * N * 4;          // one of hi / lo
+  static constexpr int kXBlockBytes = kTnEdges * 32 * 4;    // 16 edges x 32 features, row-major, one warp's block
+  static constexpr int kGHiOff = 0;
+  static constexpr int kGLoOff = kTnHiStages * kGBytes;
+  static constexpr int kXOff = kGLoOff + kTnLoStages * kGBytes;
+  static constexpr int kTileBytes = kXOff + kTnXWarps * kTnXRaw * kXBlockBytes;
+  static constexpr int kSumBytes = (kTnGWarps + 1) * 128 * 4;   // per-warp column-sum scratch (G) + odd-stage sums of X
+  static constexpr int kTotal = kTileBytes + 256 + kSumBytes + 1024;
 };
 
-// smem offset of 16-byte chunk c16 (4 features) of edge row k inside a [32 edges x F features] MN-major tile.
+// smem offset of 16-byte chunk c16 (4 features) of edge row k inside a [16 edges x F features] MN-major tile.
 // MN-major tf32 operands must use the "128B swizzle with 32-byte base" layout (CUTLASS: SW128_32B is the only
 // layout for mn-major tf32): rows of 128 B (32 features of one edge), 4-row / 512-byte atoms, and the 32-BYTE chunk
 // index inside a row XOR-ed with (row & 3)  -- Swizzle<2,5,2> on byte addresses.
@@ -80,25 +100,30 @@ __global__ void __launch_bounds__(kTnThreads, 1) tf32x3_gemm_tn_kernel(const TnP
   using L = TnSmem<M, N>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sBar = base + kTnStages * L::kStageBytes;
-  const uint32_t bar_full = sBar, bar_empty = sBar + 8 * kTnStages;
-  const uint32_t bar_acc_full = sBar + 16 * kTnStages, bar_acc_empty = bar_acc_full + 16;
+  const uint32_t sBar = base + L::kTileBytes;
+  const uint32_t bar_full = sBar, bar_done = sBar + 8 * kTnASlots;      // both indexed by stage % kTnASlots
+  const uint32_t bar_acc_full = sBar + 16 * kTnASlots, bar_acc_empty = bar_acc_full + 16;
   const uint32_t tmem_slot = bar_acc_empty + 16;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-  float* sum_scratch = reinterpret_cast<float*>(smem_raw + (sBar + 256 - smem_u32(smem_raw)));   // [2][8 warps][128]
+  float* sum_scratch = reinterpret_cast<float*>(smem_raw + (sBar + 256 - smem_u32(smem_raw)));   // [4 warps][128]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kXActive = M / 32;       // lane quadrants that hold real features (2 for M = 64)
+  const int xq = warp & 3, xh = warp >> 2;   // X producers: quadrant and stage parity
 
-  // this CTA's contiguous range of 32-edge stages
+  // this CTA's contiguous range of 16-edge stages
   const int64_t stages_total = (p.E + kTnEdges - 1) / kTnEdges;
-  const int64_t s_begin = stages_total * blockIdx.x / gridDim.x;
+  const bool interleave = (p.ablate & 32) == 0;   // stage s of CTA b = b + s * grid: neighbouring SMs stream neighbouring rows
+  const int64_t s_begin = interleave ? blockIdx.x : stages_total * blockIdx.x / gridDim.x;
   const int64_t s_end = stages_total * (blockIdx.x + 1) / gridDim.x;
-  const int64_t n_stages = s_end - s_begin;
+  const int64_t s_step = interleave ? gridDim.x : 1;
+  const int64_t n_stages = interleave ? (stages_total - blockIdx.x + gridDim.x - 1) / gridDim.x
+                                      : s_end - stages_total * blockIdx.x / gridDim.x;
   const int64_t n_flush = (n_stages + kFlushStages - 1) / kFlushStages;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kTnStages; ++s) {
-      mbar_init(bar_full + 8 * s, kTnProducerWarps);
-      mbar_init(bar_empty + 8 * s, 1);
+    for (int s = 0; s < kTnASlots; ++s) {
+      mbar_init(bar_full + 8 * s, kXActive + kTnGWarps);
+      mbar_init(bar_done + 8 * s, 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_acc_full + 8 * a, 1);
@@ -106,132 +131,201 @@ __global__ void __launch_bounds__(kTnThreads, 1) tf32x3_gemm_tn_kernel(const TnP
     }
     fence_barrier_init();
   }
-  constexpr int kTmemCols = 2 * N;
-  if (warp == kTnMmaWarp) tmem_alloc(tmem_slot, kTmemCols);
-  if constexpr (M < 128) {   // feature blocks 2,3 of every X tile are never written by the producers: zero them once
-    for (int i = threadIdx.x; i < kTnStages * 2 * (L::kXBytes / 16); i += kTnThreads) {
-      const int st = i / (2 * (L::kXBytes / 16)), rem = i % (2 * (L::kXBytes / 16));
-      const uint32_t addr = base + st * L::kStageBytes + rem * 16;
-      asm volatile("st.shared.v4.f32 [%0], {%1,%1,%1,%1};" ::"r"(addr), "f"(0.0f) : "memory");
-    }
-    fence_proxy_async();
-  }
+  if (warp == kTnMmaWarp) tmem_alloc(tmem_slot, kTnTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  if (warp > kTnMmaWarp) {
-    // =========================== PRODUCERS ===========================
-    const int pt = threadIdx.x - (kTnMmaWarp + 1) * 32;   // 0..255
-    // X tile: 16 edges x M/4 chunks of 16 B; thread handles chunk ids pt + 256*i.  A warp covers whole rows.
-    constexpr int kXChunks = kTnEdges * M / 4, kGChunks = kTnEdges * N / 4;
-    constexpr int kXPer = kXChunks / kTnProducerThreads, kGPer = kGChunks / kTnProducerThreads;   // 2 (or 1)
-    // bias gradients for free: a thread always handles the same 4 columns (256 % (M/4) == 0), so it keeps running
-    // column sums of everything it streams; rows past E are zero-filled and add nothing
-    float4 sum_x = make_float4(0.f, 0.f, 0.f, 0.f), sum_g = sum_x;
-    uint32_t offx[kXPer], offg[kGPer];
+  if (warp < 4) {
+    // =========================== X PRODUCERS: global -> raw smem block -> split -> tensor memory ===========================
+    const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16) + kTnACol;
+    if (warp >= kXActive) {
+      // M = 64: the MMA still runs with 128 rows; lanes 64..127 of the A ring are zero for the whole kernel
+      float z[32];
 #pragma unroll
-    for (int i = 0; i < kXPer; ++i) offx[i] = swz_mn((pt + kTnProducerThreads * i) / (M / 4), (pt + kTnProducerThreads * i) % (M / 4));
-#pragma unroll
-    for (int i = 0; i < kGPer; ++i) offg[i] = swz_mn((pt + kTnProducerThreads * i) / (N / 4), (pt + kTnProducerThreads * i) % (N / 4));
-    int istage = 0;
-    uint32_t iphase = 0;
+      for (int j = 0; j < 32; ++j) z[j] = 0.0f;
+      for (int s = 0; s < kTnASlots * kTnAColsPerSlot / 32; ++s) tmem_st32(t_lane + s * 32, z);
+      tmem_st_wait();
+      tc_fence_before();
+    }
+  }
+  if constexpr (kXActive < 4) {   // make those zeros visible to the MMA warp before its first instruction
+    __syncthreads();
+    tc_fence_after();
+  }
+
+  if (warp < kTnXWarps && xq < kXActive) {
+    const uint32_t t_lane = tmem_base + ((uint32_t)(xq * 32) << 16) + kTnACol;
+    const uint32_t xraw = base + L::kXOff + (uint32_t)warp * kTnXRaw * L::kXBlockBytes;
+    const bool scaled = p.row_scale != nullptr;
+    const int crow = lane >> 3, cch = lane & 7;       // this lane copies chunk cch of rows crow + 4 i
+    float sum_x = 0.0f;
+    int islot = 0;
+    // source of this lane's first chunk of the stage being issued; advanced by two stages per issue
+    const float* xsrc = p.X + ((s_begin + xh * s_step) * kTnEdges + crow) * p.ldx + xq * 32 + cch * 4;
+    const int64_t xadv = 2 * s_step * kTnEdges * p.ldx;
     auto issue = [&](int64_t st) {
-      mbar_wait(bar_empty + 8 * istage, iphase ^ 1);
-      const int64_t e0 = (s_begin + st) * kTnEdges;
-      const uint32_t x_hi = base + istage * L::kStageBytes, g_hi = x_hi + 2 * L::kXBytes;
+      const int64_t e0 = (s_begin + st * s_step) * kTnEdges;
+      const uint32_t dst = xraw + (uint32_t)islot * L::kXBlockBytes + (uint32_t)(crow * 128 + cch * 16);
+      if (!(p.ablate & (4 | 64))) {
+        if (e0 + kTnEdges <= p.E) {
 #pragma unroll
-      for (int i = 0; i < kXPer; ++i) {
-        const int c = pt + kTnProducerThreads * i;
-        const int64_t e = e0 + c / (M / 4);
-        const bool ok = e < p.E;
-        cp_async16(x_hi + offx[i], ok ? (const void*)(p.X + e * p.ldx + (c % (M / 4)) * 4) : (const void*)p.X, ok ? 16u : 0u);
-      }
+          for (int i = 0; i < kTnEdges / 4; ++i) cp_async16(dst + i * 512, xsrc + 4 * i * p.ldx, 16u);
+        } else {
 #pragma unroll
-      for (int i = 0; i < kGPer; ++i) {
-        const int c = pt + kTnProducerThreads * i;
-        const int64_t e = e0 + c / (N / 4);
-        const bool ok = e < p.E;
-        cp_async16(g_hi + offg[i], ok ? (const void*)(p.G + e * p.ldg + (c % (N / 4)) * 4) : (const void*)p.G, ok ? 16u : 0u);
+          for (int i = 0; i < kTnEdges / 4; ++i) {
+            const bool ok = e0 + crow + 4 * i < p.E;
+            cp_async16(dst + i * 512, ok ? (const void*)(xsrc + 4 * i * p.ldx) : (const void*)p.X, ok ? 16u : 0u);
+          }
+        }
       }
-      if (++istage == kTnStages) { istage = 0; iphase ^= 1; }
+      xsrc += xadv;
+      if (++islot == kTnXRaw) islot = 0;
+    };
+#pragma unroll
+    for (int d = 0; d < kTnXDepth; ++d) {
+      if (xh + 2 * d < n_stages) issue(xh + 2 * d);
+      cp_async_commit();
+    }
+    int rslot = 0, aslot = xh;
+    uint32_t aphase = 0;      // parity of the done-barrier phase that frees A slot `aslot` (valid from the second lap)
+    for (int64_t st = xh; st < n_stages; st += 2) {
+      float my_scale = 1.0f;
+      if (scaled) {
+        const int64_t e = (s_begin + st * s_step) * kTnEdges + lane;       // kTnEdges == 32: one edge per lane
+        if (e < p.E) my_scale = __ldg(p.row_scale + e);
+      }
+      cp_async_wait<kTnXDepth - 1>();
+      __syncwarp();                                            // the whole block of this warp has landed
+      if (st >= kTnASlots) mbar_wait(bar_done + 8 * aslot, aphase ^ 1);   // MMA of stage st - kTnASlots has retired
+      tc_fence_after();
+      const uint32_t src = xraw + (uint32_t)rslot * L::kXBlockBytes + (uint32_t)lane * 4;
+      const uint32_t t_slot = t_lane + aslot * kTnAColsPerSlot;
+#pragma unroll
+      for (int h16 = 0; h16 < kTnEdges / 16; ++h16) {
+        float hi[16], lo[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          float v = (p.ablate & 8) ? 0.0f : lds32(src + (h16 * 16 + r) * 128);
+          if constexpr (SX) sum_x = __fadd_rn(sum_x, v);
+          if (scaled) v = __fmul_rn(__shfl_sync(0xffffffffu, my_scale, h16 * 16 + r), v);
+          hi[r] = tf32_rna(v);
+          lo[r] = __fsub_rn(v, hi[r]);
+        }
+        tmem_st16(t_slot + h16 * 16, hi);
+        tmem_st16(t_slot + kTnEdges + h16 * 16, lo);
+      }
+      if (++rslot == kTnXRaw) rslot = 0;
+      if (st + 2 * kTnXDepth < n_stages) issue(st + 2 * kTnXDepth);   // overlaps the tcgen05.st latency
+      cp_async_commit();
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_full + 8 * aslot);
+      aslot += 2;
+      if (aslot >= kTnASlots) { aslot -= kTnASlots; aphase ^= 1; }
+    }
+    if constexpr (SX) {
+      // the two warps of a quadrant hold the even-stage and odd-stage halves of the same column sums
+      float* sx = sum_scratch + kTnGWarps * 128;
+      if (xh == 1) sx[xq * 32 + lane] = sum_x;
+      asm volatile("bar.sync 2, %0;" ::"n"(kXActive * 64) : "memory");
+      if (xh == 0) p.part_sx[(int64_t)blockIdx.x * M + xq * 32 + lane] = __fadd_rn(sum_x, sx[xq * 32 + lane]);
+    }
+  } else if (warp > kTnMmaWarp) {
+    // =========================== G PRODUCERS: global -> swizzled hi tile, lo = g - trunc(g) ===========================
+    const int gt = threadIdx.x - (kTnMmaWarp + 1) * 32;   // 0..127
+    constexpr int kGChunks = kTnEdges * N / 4;
+    constexpr int kGPer = kGChunks / kTnGThreads;          // 4 (or 2)
+    // bias gradients for free: a thread always handles the same 4 columns (128 % (N/4) == 0), so it keeps running
+    // column sums of everything it streams; rows past E are zero-filled and add nothing
+    float4 sum_g = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t offg[kGPer];
+#pragma unroll
+    for (int i = 0; i < kGPer; ++i) offg[i] = swz_mn((gt + kTnGThreads * i) / (N / 4), (gt + kTnGThreads * i) % (N / 4));
+    const uint32_t ghi = base + L::kGHiOff, glo = base + L::kGLoOff;
+    int ihi = 0;
+    // chunk i of this thread is row grow + (512 / N) i, column chunk gch: constant smem and global strides
+    constexpr int kRowStep = kTnGThreads / (N / 4);          // 4 (N = 128) or 8 (N = 64)
+    const int grow = gt / (N / 4), gch = gt % (N / 4);
+    const float* gsrc = p.G + (s_begin * kTnEdges + grow) * p.ldg + gch * 4;
+    const int64_t gadv = s_step * kTnEdges * p.ldg;
+    auto issue = [&](int64_t st) {
+      const int64_t e0 = (s_begin + st * s_step) * kTnEdges;
+      const uint32_t g_hi = ghi + (uint32_t)ihi * L::kGBytes;
+      if (!(p.ablate & (4 | 128))) {
+        if (e0 + kTnEdges <= p.E) {
+#pragma unroll
+          for (int i = 0; i < kGPer; ++i) cp_async16(g_hi + offg[i], gsrc + kRowStep * i * p.ldg, 16u);
+        } else {
+#pragma unroll
+          for (int i = 0; i < kGPer; ++i) {
+            const bool ok = e0 + grow + kRowStep * i < p.E;
+            cp_async16(g_hi + offg[i], ok ? (const void*)(gsrc + kRowStep * i * p.ldg) : (const void*)p.G, ok ? 16u : 0u);
+          }
+        }
+      }
+      gsrc += gadv;
+      if (++ihi == kTnHiStages) ihi = 0;
     };
 #pragma unroll
     for (int d = 0; d < kTnCopyDepth; ++d) {
       if (d < n_stages) issue(d);
       cp_async_commit();
     }
-    int stage = 0;
+    int shi = 0, slo = 0, fslot = 0, dslot = kTnASlots - kTnLoStages;
+    uint32_t dphase = 1;     // parity to wait for on bar_done[dslot]: stage st - kTnLoStages
     for (int64_t st = 0; st < n_stages; ++st) {
       cp_async_wait<kTnCopyDepth - 1>();                       // this thread's copies of stage `st` have landed
-      const uint32_t x_hi = base + stage * L::kStageBytes, x_lo = x_hi + L::kXBytes;
-      const uint32_t g_hi = x_lo + L::kXBytes, g_lo = g_hi + L::kGBytes;
+      // lo slot st % kTnLoStages and hi slot (st + kTnCopyDepth) % kTnHiStages were both last used by stage
+      // st - kTnLoStages: one wait covers the split's output buffer and the next copy's landing buffer
+      if (st >= kTnLoStages) mbar_wait(bar_done + 8 * dslot, dphase);
+      const uint32_t g_hi = ghi + (uint32_t)shi * L::kGBytes, g_lo = glo + (uint32_t)slo * L::kGBytes;
+      if (!(p.ablate & 8)) {
 #pragma unroll
-      for (int i = 0; i < kXPer; ++i) {
-        float4 v = lds128(x_hi + offx[i]);
-        if constexpr (SX) {
-          sum_x.x = __fadd_rn(sum_x.x, v.x); sum_x.y = __fadd_rn(sum_x.y, v.y);
-          sum_x.z = __fadd_rn(sum_x.z, v.z); sum_x.w = __fadd_rn(sum_x.w, v.w);
+        for (int i = 0; i < kGPer; ++i) {
+          const float4 v = lds128(g_hi + offg[i]);
+          if constexpr (SG) {
+            sum_g.x = __fadd_rn(sum_g.x, v.x); sum_g.y = __fadd_rn(sum_g.y, v.y);
+            sum_g.z = __fadd_rn(sum_g.z, v.z); sum_g.w = __fadd_rn(sum_g.w, v.w);
+          }
+          sts128(g_lo + offg[i], make_float4(tf32_trunc_residual(v.x), tf32_trunc_residual(v.y),
+                                             tf32_trunc_residual(v.z), tf32_trunc_residual(v.w)));
         }
-        if (p.row_scale != nullptr) {
-          const int64_t e = (s_begin + st) * kTnEdges + (pt + kTnProducerThreads * i) / (M / 4);
-          const float sc = e < p.E ? __ldg(p.row_scale + e) : 1.0f;
-          v.x = __fmul_rn(sc, v.x); v.y = __fmul_rn(sc, v.y); v.z = __fmul_rn(sc, v.z); v.w = __fmul_rn(sc, v.w);
-          sts128(x_hi + offx[i], v);
-        }
-        sts128(x_lo + offx[i], make_float4(tf32_trunc_residual(v.x), tf32_trunc_residual(v.y),
-                                           tf32_trunc_residual(v.z), tf32_trunc_residual(v.w)));
       }
-#pragma unroll
-      for (int i = 0; i < kGPer; ++i) {
-        const float4 v = lds128(g_hi + offg[i]);
-        if constexpr (SG) {
-          sum_g.x = __fadd_rn(sum_g.x, v.x); sum_g.y = __fadd_rn(sum_g.y, v.y);
-          sum_g.z = __fadd_rn(sum_g.z, v.z); sum_g.w = __fadd_rn(sum_g.w, v.w);
-        }
-        sts128(g_lo + offg[i], make_float4(tf32_trunc_residual(v.x), tf32_trunc_residual(v.y),
-                                           tf32_trunc_residual(v.z), tf32_trunc_residual(v.w)));
-      }
-      fence_proxy_async();
+      if (!(p.ablate & 1)) fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_full + 8 * stage);
-      if (++stage == kTnStages) stage = 0;
+      if (lane == 0) mbar_arrive(bar_full + 8 * fslot);
+      if (++shi == kTnHiStages) shi = 0;
+      if (++slo == kTnLoStages) slo = 0;
+      if (++fslot == kTnASlots) fslot = 0;
+      if (++dslot == kTnASlots) { dslot = 0; dphase ^= 1; }
       if (st + kTnCopyDepth < n_stages) issue(st + kTnCopyDepth);
       cp_async_commit();
     }
-    if constexpr (SX || SG) {
-      // threads with equal (pt % chunks-per-row) own the same columns: with 32 chunks per row that is one lane of each
-      // of the 8 warps; with 16 chunks per row (64 features) lanes l and l+16 of every warp as well
-      const int pw = pt >> 5;
-      float* sx = sum_scratch + pw * 128;
-      float* sg = sum_scratch + (kTnProducerWarps + pw) * 128;
-      if (M == 64) {
-        sum_x.x += __shfl_down_sync(0xffffffffu, sum_x.x, 16); sum_x.y += __shfl_down_sync(0xffffffffu, sum_x.y, 16);
-        sum_x.z += __shfl_down_sync(0xffffffffu, sum_x.z, 16); sum_x.w += __shfl_down_sync(0xffffffffu, sum_x.w, 16);
-      }
+    if constexpr (SG) {
+      // threads with equal (gt % chunks-per-row) own the same columns: with 32 chunks per row that is one lane of each
+      // of the 4 warps; with 16 chunks per row (64 features) lanes l and l+16 of every warp as well
+      const int gw = gt >> 5;
+      float* sg = sum_scratch + gw * 128;
       if (N == 64) {
         sum_g.x += __shfl_down_sync(0xffffffffu, sum_g.x, 16); sum_g.y += __shfl_down_sync(0xffffffffu, sum_g.y, 16);
         sum_g.z += __shfl_down_sync(0xffffffffu, sum_g.z, 16); sum_g.w += __shfl_down_sync(0xffffffffu, sum_g.w, 16);
       }
-      if (SX && lane < M / 4) *reinterpret_cast<float4*>(sx + 4 * lane) = sum_x;
-      if (SG && lane < N / 4) *reinterpret_cast<float4*>(sg + 4 * lane) = sum_g;
-      asm volatile("bar.sync 1, %0;" ::"n"(kTnProducerThreads) : "memory");
-      if (SX && pt < M) {
+      if (lane < N / 4) *reinterpret_cast<float4*>(sg + 4 * lane) = sum_g;
+      asm volatile("bar.sync 1, %0;" ::"n"(kTnGThreads) : "memory");
+      if (gt < N) {
         float t = 0.0f;
-        for (int w = 0; w < kTnProducerWarps; ++w) t = __fadd_rn(t, sum_scratch[w * 128 + pt]);
-        p.part_sx[(int64_t)blockIdx.x * M + pt] = t;
-      }
-      if (SG && pt < N) {
-        float t = 0.0f;
-        for (int w = 0; w < kTnProducerWarps; ++w) t = __fadd_rn(t, sum_scratch[(kTnProducerWarps + w) * 128 + pt]);
-        p.part_sg[(int64_t)blockIdx.x * N + pt] = t;
+        for (int w = 0; w < kTnGWarps; ++w) t = __fadd_rn(t, sum_scratch[w * 128 + gt]);
+        p.part_sg[(int64_t)blockIdx.x * N + gt] = t;
       }
     }
   } else if (warp == kTnMmaWarp) {
     // =========================== MMA ISSUER ===========================
     const uint32_t idesc = make_idesc_mn(128, N) ^ p.idesc_xor;
-    int stage = 0;
+    const uint32_t ghi = base + L::kGHiOff, glo = base + L::kGLoOff;
+    int shi = 0, slo = 0, aslot = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -243,70 +337,73 @@ __global__ void __launch_bounds__(kTnThreads, 1) tf32x3_gemm_tn_kernel(const TnP
       const int64_t st_hi = (st + kFlushStages < n_stages) ? st + kFlushStages : n_stages;
       bool first = true;
       for (; st < st_hi; ++st) {
-        mbar_wait(bar_full + 8 * stage, phase);
+        mbar_wait(bar_full + 8 * aslot, phase);
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t x_hi = base + stage * L::kStageBytes, x_lo = x_hi + L::kXBytes;
-          const uint32_t g_hi = x_lo + L::kXBytes, g_lo = g_hi + L::kGBytes;
+          const uint32_t g_hi = ghi + (uint32_t)shi * L::kGBytes, g_lo = glo + (uint32_t)slo * L::kGBytes;
+          const uint32_t a_hi = tmem_base + kTnACol + (uint32_t)(aslot * kTnAColsPerSlot), a_lo = a_hi + kTnEdges;
 #pragma unroll
           for (int j = 0; j < kTnEdges / 8; ++j) {
-            const uint64_t dxh = smem_desc_mn32(x_hi + j * p.kadv, p.lbo, p.sbo, p.ltype);
-            const uint64_t dxl = smem_desc_mn32(x_lo + j * p.kadv, p.lbo, p.sbo, p.ltype);
+            if (p.ablate & 2) break;
             const uint64_t dgh = smem_desc_mn32(g_hi + j * p.kadv, p.lbo, p.sbo, p.ltype);
             const uint64_t dgl = smem_desc_mn32(g_lo + j * p.kadv, p.lbo, p.sbo, p.ltype);
-            umma_tf32(d_tmem, dxl, dgh, idesc, (first && j == 0) ? 0u : 1u);
-            umma_tf32(d_tmem, dxh, dgl, idesc, 1u);
-            umma_tf32(d_tmem, dxh, dgh, idesc, 1u);
+            // small terms first, the dominant hi*hi product last
+            umma_tf32_ts(d_tmem, a_lo + j * 8, dgh, idesc, (first && j == 0) ? 0u : 1u);
+            umma_tf32_ts(d_tmem, a_hi + j * 8, dgl, idesc, 1u);
+            umma_tf32_ts(d_tmem, a_hi + j * 8, dgh, idesc, 1u);
           }
-          umma_commit(bar_empty + 8 * stage);
+          umma_commit(bar_done + 8 * aslot);
           if (st == st_hi - 1) umma_commit(bar_acc_full + 8 * acc);
         }
         __syncwarp();
         first = false;
-        if (++stage == kTnStages) { stage = 0; phase ^= 1; }
+        if (++shi == kTnHiStages) shi = 0;
+        if (++slo == kTnLoStages) slo = 0;
+        if (++aslot == kTnASlots) { aslot = 0; phase ^= 1; }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-  } else {
+  } else if (warp >= kTnXWarps && warp < kTnMmaWarp) {
     // =========================== FLUSH (TMEM -> fp32 partial in global) ===========================
-    // TMEM lane = m (feature of X), column = n (feature of G).  Warp w: lane quadrant w%4, column half w/4.
-    const int quad = warp & 3, half = warp >> 2;
+    // TMEM lane = m (feature of X), column = n (feature of G).  Warp w: lane quadrant w % 4, all N columns.
+    const int quad = warp & 3;
     const int m = quad * 32 + lane;
-    constexpr int kColsPerWarp = N / 2;
     float* part = p.partial + (int64_t)blockIdx.x * M * N + m;   // element (m, n) at n*M + m: lanes contiguous
     int acc = 0;
     uint32_t acc_phase = 0;
-    {
-      for (int64_t f = 0; f < n_flush; ++f) {
-        mbar_wait(bar_acc_full + 8 * acc, acc_phase);
-        tc_fence_after();
-        const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * N + half * kColsPerWarp);
+    for (int64_t f = 0; f < n_flush; ++f) {
+      mbar_wait(bar_acc_full + 8 * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * N);
 #pragma unroll 1
-        for (int c0 = 0; c0 < kColsPerWarp; c0 += 32) {
-          float v[32];
-          tmem_ld32(t_lane + c0, v);
-          if (m < M) {
-            float* q = part + (int64_t)(half * kColsPerWarp + c0) * M;
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        float v[32];
+        tmem_ld32(t_lane + c0, v);
+        if (m < M && !(p.ablate & 16)) {
+          float* q = part + (int64_t)c0 * M;
+          if (f != 0) {      // all 32 reads in flight before the first add (L2 latency once, not 32 times)
+            float old[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float old = (f == 0) ? 0.0f : q[j * M];
-              q[j * M] = __fadd_rn(old, v[j]);
-            }
+            for (int j = 0; j < 32; ++j) old[j] = __ldcg(q + j * M);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __fadd_rn(old[j], v[j]);
           }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) q[j * M] = v[j];
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_acc_empty + 8 * acc);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      if (n_flush == 0 && m < M) {                      // CTA without work still owns a (zero) partial
-        for (int n = half * kColsPerWarp; n < (half + 1) * kColsPerWarp; ++n) part[(int64_t)n * M] = 0.0f;
-      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acc_empty + 8 * acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (n_flush == 0 && m < M) {                      // CTA without work still owns a (zero) partial
+      for (int n = 0; n < N; ++n) part[(int64_t)n * M] = 0.0f;
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == kTnMmaWarp) tmem_dealloc(tmem_base, kTmemCols);
+  if (warp == kTnMmaWarp) tmem_dealloc(tmem_base, kTnTmemCols);
 }
 
 // D[m, n] (+)= sum over CTAs (ascending) of partial[cta][n][m]
@@ -393,7 +490,8 @@ extern "C" int dmp_gemm_tn_tf32x3(const float* X, int64_t ldx, const float* row_
   p.part_sg = colsum_g ? p.partial + grid * (M * N + M) : nullptr;
   // 4096 B between 32-feature blocks (LBO), 512 B between 4-edge atoms (SBO), 1024 B per MMA k-step (8 edges)
   p.lbo = kTnEdges * 128; p.sbo = 512; p.kadv = 1024; p.idesc_xor = 0; p.ltype = 1;
-  p.l2_prefetch = 0;
+  p.ablate = 0;
+  if (const char* ab = getenv("DMP_TN_ABLATE")) p.ablate = atoi(ab);
   if (const char* dbg = getenv("DMP_TN_DBG"))
     sscanf(dbg, "%u,%u,%u,%u,%u", &p.lbo, &p.sbo, &p.kadv, &p.idesc_xor, &p.ltype);
   cudaStream_t s = (cudaStream_t)stream;
