@@ -10,7 +10,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdmp_b200.so")
+LIB_PATH = os.environ.get("DMP_B200_LIB") or os.path.join(_HERE, "libdmp_b200.so")   # override: A/B builds
 
 # mirrors of the #defines in include/dmp_b200.h
 EID_MASK = 0x7FFFFFFF
@@ -18,6 +18,7 @@ SEG_SIGN_BY_REV = 1
 SEG_NEGATE_OUT = 2
 SEG_ONLY_FWD = 4
 SEG_ONLY_REV = 8
+SEG_SPLIT_BY_REV = 16
 ORDER_SCM = 0
 ORDER_UNC = 1
 ACT_NONE, ACT_RELU, ACT_LEAKY_RELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3, 4

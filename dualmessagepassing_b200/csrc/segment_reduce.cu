@@ -28,11 +28,15 @@ struct SegParams {
   int64_t nseg;
   int H;
   int mode;
+  int64_t split_off;   // SPLIT: column offset of the reversed-edge sums in `out` (= full H, also when H is chunked)
 };
 
-template <int VEC, int G, int ITER, int U, bool FILTER>
+// KIND: 0 plain, 1 FILTER (keep only forward / only reversed edges), 2 SPLIT (two sums per segment: forward edges into
+// out[:, 0:H], reversed edges into out[:, H:2H] -- the aggregate-first form of the node update reads every row once)
+template <int VEC, int G, int ITER, int U, int KIND>
 __global__ void __launch_bounds__(kThreads) segment_reduce_kernel(const SegParams p) {
   constexpr int kGroups = kThreads / G;
+  constexpr bool FILTER = (KIND == 1), SPLIT = (KIND == 2);
   const int lane = threadIdx.x % G;
   const int64_t seg = (int64_t)blockIdx.x * kGroups + threadIdx.x / G;
   if (seg >= p.nseg) return;
@@ -52,11 +56,14 @@ __global__ void __launch_bounds__(kThreads) segment_reduce_kernel(const SegParam
     ok[it] = col[it] < p.H;
   }
 
-  float acc[ITER][VEC];
+  float acc[ITER][VEC], acc_rev[SPLIT ? ITER : 1][VEC];
 #pragma unroll
   for (int it = 0; it < ITER; ++it)
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) acc[it][k] = 0.0f;
+    for (int k = 0; k < VEC; ++k) {
+      acc[it][k] = 0.0f;
+      if (SPLIT) acc_rev[it][k] = 0.0f;
+    }
 
   for (int j = beg; j < end; j += U) {
     uint32_t ef[U];
@@ -95,7 +102,8 @@ __global__ void __launch_bounds__(kThreads) segment_reduce_kernel(const SegParam
               float t = v[u][it].v[k];
               if (neg) t = -t;
               if (has_w) t = __fmul_rn(t, w[u]);
-              acc[it][k] = __fadd_rn(acc[it][k], t);
+              if (SPLIT && (ef[u] >> 31)) acc_rev[it][k] = __fadd_rn(acc_rev[it][k], t);
+              else acc[it][k] = __fadd_rn(acc[it][k], t);
             }
           }
         }
@@ -121,6 +129,11 @@ __global__ void __launch_bounds__(kThreads) segment_reduce_kernel(const SegParam
       for (int k = 0; k < VEC; ++k) r.v[k] = __fadd_rn(r.v[k], b.v[k]);
     }
     st_row<VEC>(p.out + seg * p.ld_out + col[it], r);
+    if constexpr (SPLIT) {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) r.v[k] = negate ? -acc_rev[it][k] : acc_rev[it][k];
+      st_row<VEC>(p.out + seg * p.ld_out + p.split_off + col[it], r);
+    }
   }
 }
 
@@ -133,8 +146,9 @@ static int launch(const SegParams& p, cudaStream_t stream) {
     set_error("segment_reduce: too many segments (%lld)", (long long)p.nseg);
     return DMP_ERR_UNSUPPORTED;
   }
-  if (filter) segment_reduce_kernel<VEC, G, ITER, U, true><<<(unsigned)blocks, kThreads, 0, stream>>>(p);
-  else segment_reduce_kernel<VEC, G, ITER, U, false><<<(unsigned)blocks, kThreads, 0, stream>>>(p);
+  if (p.mode & DMP_SEG_SPLIT_BY_REV) segment_reduce_kernel<VEC, G, ITER, U, 2><<<(unsigned)blocks, kThreads, 0, stream>>>(p);
+  else if (filter) segment_reduce_kernel<VEC, G, ITER, U, 1><<<(unsigned)blocks, kThreads, 0, stream>>>(p);
+  else segment_reduce_kernel<VEC, G, ITER, U, 0><<<(unsigned)blocks, kThreads, 0, stream>>>(p);
   return launch_status("segment_reduce_kernel");
 }
 
@@ -161,7 +175,11 @@ extern "C" int dmp_segment_reduce(const int32_t* indptr, const int32_t* eid, con
   DMP_CHECK_ARG(indptr && out, "segment_reduce: null pointer");
   DMP_CHECK_ARG(ldV >= H && ld_out >= H && (base == nullptr || ld_base >= H),
                 "segment_reduce: leading dimension smaller than H");
-  const int vec = pick_vec(H, {ldV, ld_out, base ? ld_base : 0, rev_col_offset}, {V, out, base, bias});
+  const bool split = (mode & DMP_SEG_SPLIT_BY_REV) != 0;
+  DMP_CHECK_ARG(!split || (ld_out >= 2 * H && base == nullptr && bias == nullptr &&
+                           !(mode & (DMP_SEG_ONLY_FWD | DMP_SEG_ONLY_REV))),
+                "segment_reduce: SPLIT_BY_REV writes [fwd | rev] rows of 2H floats and takes no base / bias / filter");
+  const int vec = pick_vec(H, {ldV, ld_out, base ? ld_base : 0, rev_col_offset, split ? H : 0}, {V, out, base, bias});
   const int64_t chunk = max_chunk(vec);
   for (int64_t c0 = 0; c0 < H; c0 += chunk) {
     const int64_t Hc = (H - c0 < chunk) ? (H - c0) : chunk;
@@ -180,6 +198,7 @@ extern "C" int dmp_segment_reduce(const int32_t* indptr, const int32_t* eid, con
     p.nseg = num_segments;
     p.H = (int)Hc;
     p.mode = mode;
+    p.split_off = H;
     const Shape s = pick_shape(Hc, vec);
     int rc;
     if (vec == 4) rc = dispatch<4>(p, s, (cudaStream_t)stream);

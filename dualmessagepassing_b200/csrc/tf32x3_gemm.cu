@@ -55,6 +55,8 @@ __device__ __forceinline__ uint32_t swz(int r, int c16) { return (uint32_t)(r * 
 struct GemmParams {
   const float* A; int64_t lda;
   const float* row_scale;
+  const float* epi_scale;   // accumulate mode, N == 128: the row scale is applied to the ACCUMULATOR (D += s_r * acc_r)
+                            // instead of to the streamed operand -- same product, and the producers keep their fast path
   const float* Bt; int64_t ldb;
   const float* bias;
   const float* aux; int64_t ld_aux;
@@ -208,6 +210,9 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) tf32x3_gemm_kernel(const Gemm
       // 80 KB per SM in flight, no register staging); the raw tile IS the hi operand (a kind::tf32 MMA ignores the low
       // 13 mantissa bits), the producer only adds lo = x - trunc_tf32(x).  ~2x fewer instructions per stage than the
       // register path, which was issue/latency bound (ncu: producers 58 % busy, 14 % waiting on loads).
+      // (separate hi / lo rings, 9 + 4 slots, as in tf32x3_gemm_tn.cu were tried here: store and grad modes got 12 %
+      // SLOWER -- with the bursty epilogue holding the accumulators, the 7 combined slots of split data ahead of the
+      // MMA matter more than the extra round-trip slack)
       constexpr int kCopyDepth = kStages - 2;
       uint32_t offs[4];
 #pragma unroll
@@ -524,12 +529,18 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) tf32x3_gemm_kernel(const Gemm
 #pragma unroll
             for (int j = 0; j < 32; ++j) t[j] = j < nvalid ? src[j * lds] : 0.0f;
           }
+          float sc_l = 1.0f;       // lane j holds the scale of row r0 + j; broadcast by shuffle below
+          if (MODE == kModeAccumulate && p.epi_scale != nullptr && lane < nvalid) sc_l = __ldg(p.epi_scale + r0 + lane);
           if (c == 0) {
             MBAR_WAIT(bar_acc_full + 8 * acc, acc_phase);
             tc_fence_after();
           }
           float v[32];
           tmem_ld32(t_lane + c * 32, v);
+          if (MODE == kModeAccumulate && p.epi_scale != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __fmul_rn(__shfl_sync(0xffffffffu, sc_l, j), v[j]);
+          }
           if (nvalid == 32) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) dst[j * p.ldd] = epilogue_op<MODE>(v[j], 0.0f, t[j], t[j], p.slope, act);
@@ -755,6 +766,8 @@ extern "C" int dmp_gemm_tf32x3(const float* A, int64_t lda, const float* row_sca
   else if (smooth) mode = kModeBiasSmooth;
   else if (bias != nullptr || act != DMP_ACT_NONE) mode = kModeBiasPwl;
   else mode = kModeStore;
+  p.epi_scale = nullptr;
+  if (mode == kModeAccumulate && N == 128 && row_scale != nullptr) { p.epi_scale = row_scale; p.row_scale = nullptr; }
   cudaStream_t s = (cudaStream_t)stream;
   if (N == 128 && K == 128) return launch_gemm<128, 128>(p, mode, s);
   if (N == 128 && K == 64) return launch_gemm<128, 64>(p, mode, s);
@@ -781,7 +794,7 @@ extern "C" int dmp_gemm_tf32x3_acc_gather(const float* A, int64_t lda, const flo
                 "gemm_acc_gather: operands must be 16-byte aligned");
   DMP_CHECK_ARG(A != D, "gemm_acc_gather: D must not alias A");
   GemmParams p;
-  p.A = A; p.lda = lda; p.row_scale = row_scale; p.Bt = Bt; p.ldb = ldb; p.bias = nullptr;
+  p.A = A; p.lda = lda; p.row_scale = row_scale; p.epi_scale = nullptr; p.Bt = Bt; p.ldb = ldb; p.bias = nullptr;
   p.aux = nullptr; p.ld_aux = 0; p.D = D; p.ldd = ldd; p.M = M; p.epilogue = 0; p.slope = 1.0f;
   p.g_dst = dst32; p.g_rev = rev; p.g_norm = norm; p.g_tab0 = tab_fwd; p.g_tab1 = tab_rev ? tab_rev : tab_fwd;
   p.ld_tab = ld_tab;

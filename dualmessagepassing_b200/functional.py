@@ -20,12 +20,13 @@ def _stream(t):
 
 def segment_reduce(indptr, eid, V, H, *, w_perm=None, rev_col_offset=0, base=None, bias=None, mode=0, out=None,
                    tag=None):
-    """Raw (non-differentiable) call of dmp_segment_reduce. V: [*, ldV] fp32, returns [nseg, H]."""
+    """Raw (non-differentiable) call of dmp_segment_reduce. V: [*, ldV] fp32, returns [nseg, H]
+    ([nseg, 2H] = [forward-edge sums | reversed-edge sums] with SEG_SPLIT_BY_REV)."""
     _lib.require_cuda(indptr, eid, V, w_perm, base, bias)
     V, ldV = _lib.row_major(V)
     nseg = indptr.numel() - 1
     if out is None:
-        out = torch.empty((nseg, H), dtype=torch.float32, device=V.device)
+        out = torch.empty((nseg, 2 * H if mode & _lib.SEG_SPLIT_BY_REV else H), dtype=torch.float32, device=V.device)
     ld_base = 0
     if base is not None:
         base, ld_base = _lib.row_major(base)

@@ -144,24 +144,43 @@ class _FusedDMPLayer(torch.autograd.Function):
             csc_indptr = plan.csc_indptr[n_lo:n_hi + 1]
 
         # ---- node side (dmpnn.py:113-133): project, aggregate incident edge messages, self loop, bias
-        Ln = _rowmm(X_v, nloop_w.t())
         in_t, out_t = in_w.t(), out_w.t()
-        if plan.rev_layout == "none":
-            M, m_off = _rowmm(X_e, in_t), 0
-        elif plan.rev_layout == "halves":
-            h = plan.rev_split
-            M, m_off = torch.empty((E, H), dtype=X_e.dtype, device=X_e.device), 0
-            _rowmm(X_e[:h], in_t, out=M[:h])
-            _rowmm(X_e[h:], out_t, out=M[h:])
+        Din = in_w.shape[0]
+        # Tensor-core path: AGGREGATE FIRST.  sum_e s_e n_e (X_e W) = (sum_e s_e n_e X_e) W, so one pass over X_e
+        # produces the forward-edge and reversed-edge sums per destination ([N, 2 Din]) and the projections become
+        # node-sized; the edge-sized product X_e W_in|out (41 GB of traffic at config 5) is never formed, and backward
+        # gets dW_in = A_fwd^T gN, dW_out = A_rev^T gN from the saved sums.  Same terms, different association: within
+        # the fp32 tolerance of the oracle, not bit-identical to the per-edge order (which the cuBLAS path keeps).
+        agg_first = _use_tc(X_e, in_t) and Din in (64, 128)
+        A2 = None
+        m_off = 0 if plan.rev_layout in ("none", "halves") else H   # column offset of the reversed branch in [E, 2H]
+        if agg_first:
+            split = plan.rev is not None
+            A2 = segment_reduce(csc_indptr, plan.csc_eid, X_e, Din, w_perm=norm_perm,
+                                mode=_lib.SEG_SIGN_BY_REV | (_lib.SEG_SPLIT_BY_REV if split else 0),
+                                tag="segment_reduce.node_fwd")
+            node_pre = _rowmm(X_v, nloop_w.t(), bias=nbias)
+            _rowmm(A2[:, :Din], in_t, out=node_pre, accumulate=True)
+            if split:
+                _rowmm(A2[:, Din:], out_t, out=node_pre, accumulate=True)
         else:
-            # two-branch buffer [E, 2H]: both projections, the kernel picks the half by the edge's flag
-            M, m_off = torch.empty((E, 2 * H), dtype=X_e.dtype, device=X_e.device), H
-            _rowmm(X_e, in_t, out=M[:, :H])
-            _rowmm(X_e, out_t, out=M[:, H:])
-        node_pre = segment_reduce(csc_indptr, plan.csc_eid, M, H, w_perm=norm_perm, rev_col_offset=m_off,
-                                  base=Ln, bias=nbias, mode=_lib.SEG_SIGN_BY_REV, out=Ln,
-                                  tag="segment_reduce.node_fwd")
-        del M
+            Ln = _rowmm(X_v, nloop_w.t())
+            if plan.rev_layout == "none":
+                M = _rowmm(X_e, in_t)
+            elif plan.rev_layout == "halves":
+                h = plan.rev_split
+                M = torch.empty((E, H), dtype=X_e.dtype, device=X_e.device)
+                _rowmm(X_e[:h], in_t, out=M[:h])
+                _rowmm(X_e[h:], out_t, out=M[h:])
+            else:
+                # two-branch buffer [E, 2H]: both projections, the kernel picks the half by the edge's flag
+                M = torch.empty((E, 2 * H), dtype=X_e.dtype, device=X_e.device)
+                _rowmm(X_e, in_t, out=M[:, :H])
+                _rowmm(X_e, out_t, out=M[:, H:])
+            node_pre = segment_reduce(csc_indptr, plan.csc_eid, M, H, w_perm=norm_perm, rev_col_offset=m_off,
+                                      base=Ln, bias=nbias, mode=_lib.SEG_SIGN_BY_REV, out=Ln,
+                                      tag="segment_reduce.node_fwd")
+            del M
 
         # ---- edge side (dmpnn.py:112-123,142-149): endpoint gather, degree term, self loop, bias
         Qd = _rowmm(X_v_full, dst_w.t())
@@ -184,7 +203,7 @@ class _FusedDMPLayer(torch.autograd.Function):
         ctx.X_v_full = X_v_full if part is not None else None
         ctx.save_for_backward(X_v, X_e, in_w, out_w, src_w, dst_w, nloop_w, eloop_w, nW1, nW2, eW1, eW2,
                               node_pre, nh1, edge_pre, eh1,
-                              node_out if not has_mlp else None, edge_out if not has_mlp else None)
+                              node_out if not has_mlp else None, edge_out if not has_mlp else None, A2)
         ctx.has_bias = (nbias is not None, ebias is not None)
         ctx.mlp_bias = (nb1 is not None, nb2 is not None, eb1 is not None, eb2 is not None)
         return node_out, edge_out
@@ -192,7 +211,7 @@ class _FusedDMPLayer(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_node_out, g_edge_out):
         (X_v, X_e, in_w, out_w, src_w, dst_w, nloop_w, eloop_w, nW1, nW2, eW1, eW2,
-         node_pre, nh1, edge_pre, eh1, node_act, edge_act) = ctx.saved_tensors
+         node_pre, nh1, edge_pre, eh1, node_act, edge_act, A2) = ctx.saved_tensors
         plan = ctx.plan
         if getattr(ctx, "consumed", False):
             raise RuntimeError("the fused DMPNN layer re-uses its saved buffers in backward and cannot be "
@@ -235,8 +254,7 @@ class _FusedDMPLayer(torch.autograd.Function):
         Din = in_w.shape[0]
         # Gradient of the node aggregation w.r.t. the edge side.  On the tensor-core path nothing edge-sized is
         # materialised for it: dX_e receives  sgn*norm*(gN W_n^T)[dst]  from node-sized tables inside the GEMM epilogue
-        # and dW_in / dW_out come from aggregate-first sums (segment reduce of X_e by destination, then a node-sized
-        # reduction).  Otherwise T = sgn*norm*gN[dst] is written out and fed to plain GEMMs.
+        # and dW_in / dW_out come from the aggregate-first sums A2 saved by forward (a node-sized reduction each).  Otherwise T = sgn*norm*gN[dst] is written out and fed to plain GEMMs.
         gather = (need_xe or need_w) and _use_tc(gE, w_sd) and Din in (64, 128)
         T = None
         if not gather:
@@ -301,16 +319,13 @@ class _FusedDMPLayer(torch.autograd.Function):
             d_src = _tnmm(X_v_full, dQs)
             d_src.add_(d_sd)
             if gather:
-                seg_ptr = plan.csc_indptr if part is None else plan.csc_indptr[part[0]:part[1] + 1]
-                a_in = segment_reduce(seg_ptr, plan.csc_eid, X_e, Din, w_perm=ctx.norm_perm,
-                                      mode=_lib.SEG_SIGN_BY_REV | _lib.SEG_ONLY_FWD, tag="segment_reduce.dWin_bwd")
-                d_in = _tnmm(a_in, gN)
-                if plan.rev is not None:
-                    a_out = segment_reduce(seg_ptr, plan.csc_eid, X_e, Din, w_perm=ctx.norm_perm,
-                                           mode=_lib.SEG_SIGN_BY_REV | _lib.SEG_ONLY_REV, tag="segment_reduce.dWout_bwd")
-                    d_out = _tnmm(a_out, gN)
-                else:
-                    d_out = torch.zeros_like(out_w)
+                if A2 is None:   # forward did not run aggregate-first: rebuild the per-destination sums of X_e
+                    seg_ptr = plan.csc_indptr if part is None else plan.csc_indptr[part[0]:part[1] + 1]
+                    A2 = segment_reduce(seg_ptr, plan.csc_eid, X_e, Din, w_perm=ctx.norm_perm,
+                                        mode=_lib.SEG_SIGN_BY_REV | (_lib.SEG_SPLIT_BY_REV if plan.rev is not None else 0),
+                                        tag="segment_reduce.dW_bwd")
+                d_in = _tnmm(A2[:, :Din], gN)
+                d_out = _tnmm(A2[:, Din:], gN) if plan.rev is not None else torch.zeros_like(out_w)
             elif plan.rev_layout == "none":
                 d_in = _tnmm(X_e, T)
                 d_out = torch.zeros_like(out_w)

@@ -49,6 +49,11 @@ extern "C" {
 #define DMP_SEG_NEGATE_OUT 2  /* out = -(sum)  (used for dQ_s = -SB in backward)                         */
 #define DMP_SEG_ONLY_FWD 4    /* skip reversed edges (their rows are not even loaded)                     */
 #define DMP_SEG_ONLY_REV 8    /* skip forward edges                                                        */
+#define DMP_SEG_SPLIT_BY_REV 16 /* two sums per segment in one pass: forward edges -> out[:, 0:H], reversed edges ->
+                                   out[:, H:2H] (ld_out >= 2H; no base / bias / filter).  Each half equals the
+                                   ONLY_FWD / ONLY_REV result bit for bit.  By linearity of the node update
+                                   sum_e s_e n_e (X_e W) = (sum_e s_e n_e X_e) W  (dmpnn.py:113-133) this replaces the
+                                   edge-sized projection by two node-sized ones. */
 
 /* dmp_edge_update order */
 #define DMP_ORDER_SCM 0 /* ((eloop + add) + agg) + ebias   dmpnn.py:147-149  */
@@ -170,7 +175,9 @@ DMP_API int dmp_gate_residual_backward(const float* gout, int64_t ld_gout, const
  *                                                                 nn.Linear layout ([out, in], row-major)
  * Replaces the per-edge `th.matmul(...)` calls of dmpnn.py:112-113,120-121,146-147 and the MLP Linears
  * (dmpnn.py:45-52) and their autograd transposes.  row_scale [M] (may be NULL) multiplies each row of A
- * first, as a separately rounded fp32 product (fuses `coef ⊙ gE`).  epilogue = DMP_ACT_* id, optionally
+ * first, as a separately rounded fp32 product (fuses `coef ⊙ gE`); with DMP_EPI_ACCUMULATE and N = 128 the same
+ * factor is applied to the accumulated row instead (D[r,:] += row_scale[r] * (A[r,:]·Bt^T): equal up to fp32
+ * rounding, and the streaming side of the kernel keeps its copy-only fast path).  epilogue = DMP_ACT_* id, optionally
  * OR-ed with DMP_EPI_MUL_ACT_GRAD (D = acc * act'(aux), aux = activation OUTPUT [M,N]) and/or
  * DMP_EPI_ACCUMULATE (D += result).  bias [N] may be NULL.  D must not alias A.
  */

@@ -22,22 +22,25 @@
 void oracle_seg_reduce(const int32_t* indptr, const uint32_t* eid, const float* w_perm, const float* V,
                        int64_t ldV, int64_t rev_off, const float* base, int64_t ld_base, const float* bias,
                        float* out, int64_t ld_out, int64_t nseg, int64_t H, int mode) {
-  float* acc = (float*)malloc(sizeof(float) * (size_t)(H > 0 ? H : 1));
+  /* mode & 16 (SPLIT_BY_REV): forward edges accumulate into out[x, 0:H], reversed edges into out[x, H:2H] */
+  float* acc = (float*)malloc(sizeof(float) * (size_t)(H > 0 ? 2 * H : 1));
+  const int split = (mode & 16) != 0;
   for (int64_t x = 0; x < nseg; ++x) {
-    for (int64_t h = 0; h < H; ++h) acc[h] = 0.0f;
+    for (int64_t h = 0; h < 2 * H; ++h) acc[h] = 0.0f;
     for (int32_t j = indptr[x]; j < indptr[x + 1]; ++j) {
       uint32_t r = eid[j] >> 31;
       if (((mode & 4) && r) || ((mode & 8) && !r)) continue; /* ONLY_FWD / ONLY_REV */
       const float* row = V + (int64_t)(eid[j] & EID_MASK) * ldV + (r ? rev_off : 0);
       int neg = (mode & 1) && !r;
+      float* a = acc + ((split && r) ? H : 0);
       for (int64_t h = 0; h < H; ++h) {
         float t = row[h];
         if (neg) t = -t;
         if (w_perm) t = t * w_perm[j];
-        acc[h] = acc[h] + t;
+        a[h] = a[h] + t;
       }
     }
-    for (int64_t h = 0; h < H; ++h) {
+    for (int64_t h = 0; h < (split ? 2 * H : H); ++h) {
       float r = (mode & 2) ? -acc[h] : acc[h];
       if (base) r = base[x * ld_base + h] + r;
       if (bias) r = r + bias[h];

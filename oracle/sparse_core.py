@@ -36,10 +36,10 @@ def _i64(x):
 
 def seg_reduce(indptr, eid, V, H, *, w_perm=None, rev_off=0, base=None, bias=None, mode=0, ldV=None):
     nseg = indptr.numel() - 1
-    out = torch.empty((nseg, H), dtype=torch.float32)
+    out = torch.empty((nseg, 2 * H if mode & 16 else H), dtype=torch.float32)   # 16 = SPLIT_BY_REV: [fwd | rev]
     ldV = V.stride(0) if ldV is None else ldV
     lib().oracle_seg_reduce(_p(indptr), _p(eid), _p(w_perm), _p(V), _i64(ldV), _i64(rev_off), _p(base),
-                            _i64(base.stride(0) if base is not None else 0), _p(bias), _p(out), _i64(H),
+                            _i64(base.stride(0) if base is not None else 0), _p(bias), _p(out), _i64(out.stride(0)),
                             _i64(nseg), _i64(H), ctypes.c_int(mode))
     return out
 

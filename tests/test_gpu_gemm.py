@@ -64,6 +64,11 @@ def test_gemm_epilogues(act, slope):
     D = D0.clone()
     F.gemm_tf32x3(A, Wt, out=D, accumulate=True)
     assert torch.equal(D, D0 + plain)
+    # accumulate with a row scale: N = 128 scales the accumulated row (exactly D0 + s * (A W^T)), N = 64 scales A
+    D = D0.clone()
+    F.gemm_tf32x3(A, Wt, out=D, accumulate=True, row_scale=scale)
+    want = D0 + scale.unsqueeze(1) * plain if N == 128 else D0 + F.gemm_tf32x3(scale.unsqueeze(1) * A, Wt)
+    assert torch.equal(D, want)
     # act'(output) multiply (MLP backward)
     y = fn(torch.randn(M, N, device="cuda", generator=g))
     got = F.gemm_tf32x3(A, Wt, act=act, slope=slope, aux=y, mul_act_grad=True)

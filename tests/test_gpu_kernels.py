@@ -203,3 +203,29 @@ def test_segment_reduce_flag_filters_bit_exact(H):
         assert torch.equal(got.cpu(), want)
     both = sc.seg_reduce(cp["csc_indptr"], cp["csc_eid"], X, H, w_perm=w_cpu, mode=_lib.SEG_SIGN_BY_REV)
     assert float(both.abs().sum()) > 0
+
+
+@pytest.mark.parametrize("H", [8, 32, 64, 128, 200])
+def test_segment_reduce_split_by_rev_bit_exact(H):
+    """SPLIT_BY_REV (aggregate-first node update): one pass, [forward sums | reversed sums]; each half equals the
+    filtered reduce and the C oracle bit for bit, also with strided rows."""
+    from dualmessagepassing_b200 import _lib, functional as F
+    s, d, r = make_graph(seed=7 + H, n=257, e0=3000, rev="shuffled")
+    plan = _plan(s, d, 257, r)
+    cp = _cpu_plan(plan)
+    E = len(s)
+    g = torch.Generator().manual_seed(H)
+    Xw, norm = torch.randn(E, H + 8, generator=g), torch.rand(E, generator=g)
+    X = Xw[:, :H]                                             # ldV = H + 8
+    w_cpu = norm[(cp["csc_eid"].long() & 0x7FFFFFFF)]
+    w_gpu = plan.norm_permuted(norm.cuda())[1]
+    mode = _lib.SEG_SIGN_BY_REV | _lib.SEG_SPLIT_BY_REV
+    want = sc.seg_reduce(cp["csc_indptr"], cp["csc_eid"], X, H, w_perm=w_cpu, mode=mode)
+    got = F.segment_reduce(plan.csc_indptr, plan.csc_eid, Xw.cuda()[:, :H], H, w_perm=w_gpu, mode=mode)
+    assert got.shape == (257, 2 * H) and torch.equal(got.cpu(), want)
+    for filt, half in ((_lib.SEG_ONLY_FWD, got[:, :H]), (_lib.SEG_ONLY_REV, got[:, H:])):
+        one = F.segment_reduce(plan.csc_indptr, plan.csc_eid, Xw.cuda()[:, :H], H, w_perm=w_gpu,
+                               mode=_lib.SEG_SIGN_BY_REV | filt)
+        assert torch.equal(one, half)
+    with pytest.raises(RuntimeError):
+        F.segment_reduce(plan.csc_indptr, plan.csc_eid, X.cuda(), H, mode=mode, bias=torch.zeros(H, device="cuda"))

@@ -42,6 +42,13 @@ def test_seg_reduce_equals_torch_index_add_in_edge_order():
     msg = (sgn * M) * norm.unsqueeze(1)
     want = (base + torch.zeros(40, H).index_add(0, torch.from_numpy(d), msg)) + bias
     assert torch.equal(got, want)
+    # SPLIT_BY_REV (16): [sum over forward edges | sum over reversed edges], each an index_add over its subset
+    split = sc.seg_reduce(indptr, eid, M, H, w_perm=w_perm, mode=1 | 16)
+    rt, dt = torch.from_numpy(r), torch.from_numpy(d)
+    for half, keep in ((split[:, :H], ~rt), (split[:, H:], rt)):
+        assert torch.equal(half, torch.zeros(40, H).index_add(0, dt[keep], msg[keep]))
+    assert torch.equal(split[:, :H], sc.seg_reduce(indptr, eid, M, H, w_perm=w_perm, mode=1 | 4))
+    assert torch.equal(split[:, H:], sc.seg_reduce(indptr, eid, M, H, w_perm=w_perm, mode=1 | 8))
 
 
 def test_edge_update_and_backward_equal_torch_expressions():
