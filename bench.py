@@ -380,6 +380,8 @@ def run_ours(args):
     # ---- per-kernel durations -> roofline of the dominant hand-written kernel ----------------------------
     by_tag, bytes_by_tag = {}, {}
     for tag, e_0, e_1, nb in prof:
+        if tag.startswith("gemm") and nb is not None:
+            tag += "@E" if nb >= nE * h * 4 else "@N"   # edge-sized and node-sized launches are different regimes
         by_tag.setdefault(tag, []).append(e_0.elapsed_time(e_1))
         if nb is not None:
             bytes_by_tag[tag] = bytes_by_tag.get(tag, 0) + nb
@@ -400,9 +402,17 @@ def run_ours(args):
     if cand:
         top = max(cand, key=lambda k: cand[k]["avg_ms"] * cand[k]["launches_per_step"])
         kv = cand[top]
+        # DRAM bytes of one full-size launch of that kernel from the committed `ncu --set full` capture (only valid
+        # for the workload it was taken on)
+        traffic, traffic_src = None, None
+        tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")
+        if args.workload == "cfg5" and world == 1 and os.path.exists(tpath):
+            tk = json.load(open(tpath))["kernels"].get(top.replace("@E", ""))
+            if tk is not None and (top.endswith("@E") or not top.startswith("gemm")):
+                traffic, traffic_src = tk["traffic_bytes"], "profiles/r1_traffic.json (%s)" % tk["kernel"]
         roofline = {"kernel": top, "bound": "hbm", "achieved": kv["gbs"], "peak": hbm_peak, "unit": "GB/s",
-                    "frac": kv["frac"], "traffic": None, "alg_bytes_per_launch": kv["alg_bytes"],
-                    "avg_launch_ms": kv["avg_ms"], "peak_source": peak_src}
+                    "frac": kv["frac"], "traffic": traffic, "traffic_source": traffic_src,
+                    "alg_bytes_per_launch": kv["alg_bytes"], "avg_launch_ms": kv["avg_ms"], "peak_source": peak_src}
         sp = {k: v for k, v in cand.items() if not k.startswith("gemm")}
         sparse_ms = sum(v["avg_ms"] * v["launches_per_step"] for v in sp.values())
         sparse_bytes = sum(v["alg_bytes"] * v["launches_per_step"] for v in sp.values())

@@ -1,10 +1,14 @@
 """Turn gpurun_out ncu captures into the committed summaries under profiles/ (run here, no GPU needed).
 
-    python scripts/summarise_ncu.py <launches.csv> <full.ncu-rep> <out.md>
+    python scripts/summarise_ncu.py <launches.csv> <full.ncu-rep> <out.md> [<traffic.json>]
+
+With a fourth argument the DRAM bytes of the full-size launches (scripts/ncu_kernels_fullsize.py, one launch per bench
+tag, in TAGS order) are also written as JSON; bench.py reads that file to fill `roofline.traffic`.
 """
 import collections, csv, io, subprocess, sys
 
 launch_csv, rep, out = sys.argv[1:4]
+traffic_json = sys.argv[4] if len(sys.argv) > 4 else None
 lines = [l for l in open(launch_csv) if not l.startswith("==")]
 agg, total, n = collections.OrderedDict(), 0.0, 0
 for row in csv.DictReader(io.StringIO("".join(lines))):
@@ -35,7 +39,7 @@ seen = set()
 for r in rows[2:]:
     name = r[idx["Kernel Name"]].split("(")[0][:70]
     key = (name, r[idx["launch__grid_size"]])
-    if key in seen:
+    if key in seen and traffic_json is None:
         continue
     seen.add(key)
     vals = []
@@ -49,3 +53,19 @@ for r in rows[2:]:
     md.append("| `%s` | " % name + " | ".join(vals) + " |")
 open(out, "w").write("\n".join(md) + "\n")
 print("\n".join(md[-14:]))
+
+if traffic_json:
+    import json
+    sys.path.insert(0, "scripts")
+    from ncu_kernels_fullsize import TAGS
+    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+    body = rows[2:]
+    assert len(body) == len(TAGS), (len(body), len(TAGS))
+    outj = {"source": rep, "note": "one full-size (config 5) launch per tag, ncu --set full --clock-control none; bytes per launch",
+            "kernels": {}}
+    for tag, r in zip(TAGS, body):
+        rd = float(r[idx["dram__bytes_read.sum"]]) * scale[units[idx["dram__bytes_read.sum"]]]
+        wr = float(r[idx["dram__bytes_write.sum"]]) * scale[units[idx["dram__bytes_write.sum"]]]
+        outj["kernels"][tag] = {"kernel": r[idx["Kernel Name"]].split("(")[0], "dram_read_bytes": rd, "dram_write_bytes": wr,
+                                "traffic_bytes": rd + wr, "ncu_time_ms": float(r[idx["gpu__time_duration.sum"]])}
+    json.dump(outj, open(traffic_json, "w"), indent=1)
