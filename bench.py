@@ -60,6 +60,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the secondary train graphs/sec measurement")
+    ap.add_argument("--no-mlp0", action="store_true", help="skip the num_mlp_layers=0 variant of the layer")
     ap.add_argument("--train-config", default="cfg2", choices=["cfg1", "cfg2", "cfg3"])
     ap.add_argument("--train-steps", type=int, default=30)
     ap.add_argument("--cpu-sample-edges", type=int, default=0, help="override the CPU sample size (edges incl. reversed)")
@@ -377,6 +378,29 @@ def run_ours(args):
     ms_per_step = float(t.item()) / args.steps
     value = E / (ms_per_step * 1e-3)
 
+    # ---- same graph, MLP-less layer ("report both num_mlp_layers=2 and 0") ---------------------
+    mlp0 = None
+    if world == 1 and not args.no_mlp0:
+        layer2, params2 = layer, params
+        torch.manual_seed(5001)
+        layer = dmp.DMPLayer(h, h, num_mlp_layers=0, batch_norm=False, act_func="leaky_relu").to(dev)
+        params = [p for p in layer.parameters()]
+        k0 = min(args.steps, 5)
+        for _ in range(3):
+            step(xv, xe)
+        barrier()
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        m0.record()
+        for _ in range(k0):
+            step(xv, xe)
+        m1.record()
+        barrier()
+        ms0 = m0.elapsed_time(m1) / k0
+        mlp0 = {"layer": "DMPLayer(%d,%d,num_mlp_layers=0,act_func=leaky_relu)" % (h, h), "ms_per_step": ms0,
+                "value": E / (ms0 * 1e-3), "unit": "edges/s", "steps": k0}
+        layer, params = layer2, params2
+        del layer2, params2
+
     # ---- per-kernel durations -> roofline of the dominant hand-written kernel ----------------------------
     by_tag, bytes_by_tag = {}, {}
     for tag, e_0, e_1, nb in prof:
@@ -507,7 +531,7 @@ def run_ours(args):
                        "dense": "projections on tcgen05 tensor cores, 3xTF32 split with fp32 accumulation "
                                 "(fp32-level accuracy: 1.2e-6 vs fp64; cuBLAS sgemm 5e-7); sparse core in fp32"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
-            "clocks": clocks, "kernels": kernels, "train": train,
+            "clocks": clocks, "kernels": kernels, "mlp0": mlp0, "train": train,
             "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9,
         }
         print(json.dumps(line), flush=True)

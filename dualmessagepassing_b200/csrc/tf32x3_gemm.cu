@@ -222,22 +222,37 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) tf32x3_gemm_kernel(const Gemm
       // per-row scales of the tile (same 4 rows for all k-blocks): fetched when the tile's first k-block is ISSUED
       // (kCopyDepth stages ahead of its use), double-buffered by tile parity so the fetch latency is never exposed
       float sc_a[4] = {1.f, 1.f, 1.f, 1.f}, sc_b[4] = {1.f, 1.f, 1.f, 1.f};
-      auto issue = [&](int64_t it) {
+      // source of this thread's first chunk of the k-block being issued, advanced incrementally (no 64-bit multiplies
+      // per copy): + kKB floats per k-block, + gridDim.x tiles after the last k-block of a tile
+      const float* asrc = p.A + ((int64_t)blockIdx.x * kTileM + row0) * p.lda + c16 * 4;
+      const int64_t lda32 = 32 * p.lda;
+      const int64_t tile_adv = (int64_t)gridDim.x * kTileM * p.lda - (kKBlocks - 1) * kKB;
+      int64_t irow0 = (int64_t)blockIdx.x * kTileM;    // first row of the tile being issued
+      int ikb = 0;
+      uint32_t itl = 0;                                // parity of the local tile index
+      auto issue = [&](int64_t) {
         MBAR_WAIT(bar_empty + 8 * istage, iphase ^ 1);
-        const int64_t tl = it / kKBlocks;
-        const int64_t tile = (int64_t)blockIdx.x + tl * gridDim.x;
-        const int kb = (int)(it % kKBlocks);
         const uint32_t hi = sA + istage * L::kStageBytes;
+        if (irow0 + kTileM <= p.M) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int64_t r = tile * kTileM + row0 + 32 * i;
-          const bool ok = r < p.M;
-          cp_async16(hi + offs[i], ok ? (const void*)(p.A + r * p.lda + kb * kKB + c16 * 4) : (const void*)p.A, ok ? 16u : 0u);
-          if (kb == 0 && p.row_scale != nullptr) {
-            const float v = ok ? __ldg(p.row_scale + r) : 1.0f;
-            if (tl & 1) sc_b[i] = v; else sc_a[i] = v;
+          for (int i = 0; i < 4; ++i) cp_async16(hi + offs[i], asrc + i * lda32, 16u);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const bool ok = irow0 + row0 + 32 * i < p.M;
+            cp_async16(hi + offs[i], ok ? (const void*)(asrc + i * lda32) : (const void*)p.A, ok ? 16u : 0u);
           }
         }
+        if (ikb == 0 && p.row_scale != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int64_t r = irow0 + row0 + 32 * i;
+            const float v = r < p.M ? __ldg(p.row_scale + r) : 1.0f;
+            if (itl & 1) sc_b[i] = v; else sc_a[i] = v;
+          }
+        }
+        if (++ikb == kKBlocks) { ikb = 0; asrc += tile_adv; irow0 += (int64_t)gridDim.x * kTileM; itl ^= 1; }
+        else asrc += kKB;
         if (++istage == kStages) { istage = 0; iphase ^= 1; }
       };
       auto l2_prefetch_tile = [&](int64_t local_tile) {
