@@ -182,7 +182,7 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def kernel_bytes(tag, N, E, H, has_norm=False):
+def kernel_bytes(tag, N, E, H, has_norm=False, mirrored=False):
     """Algorithmic bytes of one launch of each hand-written kernel ('Kernels')."""
     row = 4 * H
     if tag == "segment_reduce.node_fwd":
@@ -190,7 +190,8 @@ def kernel_bytes(tag, N, E, H, has_norm=False):
     if tag.startswith("segment_reduce"):
         return E * row + N * row + 4 * E + 4 * (N + 1)
     if tag == "edge_update":
-        return 5 * E * row + 12 * E + row
+        # S, P, out per edge + the two endpoint rows: fetched once per mirrored PAIR of edges (e, e + E/2) on one graph
+        return (4 if mirrored else 5) * E * row + 12 * E + row
     if tag == "edge_backward":
         return 2 * E * row + 5 * E   # gather gN[dst] + write T (coef*gE is folded into the GEMM prologues)
     if tag == "act_inplace":
@@ -413,7 +414,7 @@ def run_ours(args):
     for tag, ms in by_tag.items():
         # algorithmic bytes: fixed-shape kernels from the table in DESIGN.md, GEMM launches report their own
         # (operands + result, shapes differ per launch) -> average bytes per launch
-        nb = bytes_by_tag[tag] / len(ms) if tag in bytes_by_tag else kernel_bytes(tag, nN, nE, h)
+        nb = bytes_by_tag[tag] / len(ms) if tag in bytes_by_tag else kernel_bytes(tag, nN, nE, h, mirrored=(world == 1))
         avg = float(np.mean(ms))
         entry = {"launches_per_step": len(ms) / args.steps, "avg_ms": avg, "share_of_step": sum(ms) / total_ms}
         if nb is not None:

@@ -21,6 +21,7 @@ SEG_ONLY_REV = 8
 SEG_SPLIT_BY_REV = 16
 ORDER_SCM = 0
 ORDER_UNC = 1
+EDGE_MIRRORED_HALVES = 16
 ACT_NONE, ACT_RELU, ACT_LEAKY_RELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3, 4
 ACT_FROM_OUTPUT = 16
 EPI_MUL_ACT_GRAD = 32

@@ -90,6 +90,77 @@ __global__ void __launch_bounds__(kThreads) edge_update_kernel(const EdgeFwdPara
   }
 }
 
+// Mirrored halves: after `add_reversed_edges` on one graph (SCM/train.py:299-327) edge e + E/2 is the reverse of edge
+// e, and its endpoint ROLES coincide (a = dst of the original, b = its src), so both rows gather the same Q_d / Q_s
+// rows.  One group handles the pair and fetches the two table rows once: 4 instead of 5 row-reads+writes per edge.  The
+// indices of both rows are compared, a pair that does not match simply loads its own rows -> always correct.
+template <int VEC, int G, int ITER>
+__global__ void __launch_bounds__(kThreads, 4) edge_update_pair_kernel(const EdgeFwdParams p) {
+  constexpr int kGroups = kThreads / G;
+  const int lane = threadIdx.x % G;
+  const int64_t stride = (int64_t)gridDim.x * kGroups;
+  const int64_t half = p.E / 2;
+  int col[ITER];
+  bool ok[ITER];
+  Row<VEC> bias[ITER];
+#pragma unroll
+  for (int it = 0; it < ITER; ++it) {
+    col[it] = (lane + it * G) * VEC;
+    ok[it] = col[it] < p.H;
+    if (ok[it] && p.ebias != nullptr) bias[it] = ld_row<VEC>(p.ebias + col[it]);
+  }
+#pragma unroll 1
+  for (int64_t e = (int64_t)blockIdx.x * kGroups + threadIdx.x / G; e < half; e += stride) {
+    const int64_t e2 = e + half;
+    const int a = __ldg(p.a32 + e), b = __ldg(p.b32 + e);
+    const int a2 = __ldg(p.a32 + e2), b2 = __ldg(p.b32 + e2);
+    const float c = __ldg(p.coef + e), c2 = __ldg(p.coef + e2);
+    const float* qd_row = p.Qd + (int64_t)a * p.ldQd;
+    const float* qs_row = p.Qs + (int64_t)b * p.ldQs;
+    Row<VEC> s[ITER], pp[ITER], s2[ITER], pp2[ITER], qd[ITER], qs[ITER];
+#pragma unroll
+    for (int it = 0; it < ITER; ++it) {
+      if (ok[it]) {
+        qd[it] = ld_row<VEC>(qd_row + col[it]);
+        qs[it] = ld_row<VEC>(qs_row + col[it]);
+        s[it] = ld_plain<VEC>(p.S + e * p.ldS + col[it]);     // may alias out
+        pp[it] = ld_stream<VEC>(p.P + e * p.ldP + col[it]);
+        s2[it] = ld_plain<VEC>(p.S + e2 * p.ldS + col[it]);
+        pp2[it] = ld_stream<VEC>(p.P + e2 * p.ldP + col[it]);
+      }
+    }
+    auto emit = [&](int64_t row, float cc, const Row<VEC> (&sv)[ITER], const Row<VEC> (&pv)[ITER]) {
+#pragma unroll
+      for (int it = 0; it < ITER; ++it) {
+        if (!ok[it]) continue;
+        Row<VEC> o;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          const float msg = __fsub_rn(qd[it].v[k], qs[it].v[k]);
+          const float add = __fmul_rn(cc, pv[it].v[k]);
+          float t;
+          if (p.order == DMP_ORDER_SCM) t = __fadd_rn(__fadd_rn(sv[it].v[k], add), msg);
+          else t = __fadd_rn(__fadd_rn(sv[it].v[k], msg), add);
+          if (p.ebias != nullptr) t = __fadd_rn(t, bias[it].v[k]);
+          o.v[k] = t;
+        }
+        st_stream<VEC>(p.out + row * p.ld_out + col[it], o);
+      }
+    };
+    emit(e, c, s, pp);
+    if (a2 != a || b2 != b) {     // not a mirrored pair (group-uniform): fetch the second row's own table rows
+#pragma unroll
+      for (int it = 0; it < ITER; ++it) {
+        if (ok[it]) {
+          qd[it] = ld_row<VEC>(p.Qd + (int64_t)a2 * p.ldQd + col[it]);
+          qs[it] = ld_row<VEC>(p.Qs + (int64_t)b2 * p.ldQs + col[it]);
+        }
+      }
+    }
+    emit(e2, c2, s2, pp2);
+  }
+}
+
 // ---- backward edge gather ----------------------------------------------------------------------------
 struct EdgeBwdParams {
   const int32_t* dst32;
@@ -267,6 +338,8 @@ extern "C" int dmp_edge_update(const int32_t* a32, const int32_t* b32, const flo
   DMP_CHECK_ARG(num_edges >= 0 && H >= 0, "edge_update: negative size");
   if (num_edges == 0 || H == 0) return DMP_OK;
   DMP_CHECK_ARG(a32 && b32 && coef && S && P && Qd && Qs && out, "edge_update: null pointer");
+  const bool pair = (order & DMP_EDGE_MIRRORED_HALVES) != 0 && num_edges % 2 == 0;
+  order &= ~DMP_EDGE_MIRRORED_HALVES;
   DMP_CHECK_ARG(order == DMP_ORDER_SCM || order == DMP_ORDER_UNC, "edge_update: bad order %d", order);
   DMP_CHECK_ARG(ldS >= H && ldP >= H && ldQd >= H && ldQs >= H && ld_out >= H && (!edge_agg || ld_agg >= H),
                 "edge_update: leading dimension smaller than H");
@@ -283,7 +356,24 @@ extern "C" int dmp_edge_update(const int32_t* a32, const int32_t* b32, const flo
     p.out = out + c0; p.ld_out = ld_out;
     p.agg = edge_agg ? edge_agg + c0 : nullptr; p.ld_agg = ld_agg;
     p.E = num_edges; p.H = (int)((H - c0 < chunk) ? (H - c0) : chunk); p.order = order;
-    DMP_DISPATCH_SHAPE(edge_update_kernel, p, num_edges, (cudaStream_t)stream);
+    const Shape sh = pick_shape(p.H, vec);
+    if (pair && sh.iter == 1 && edge_agg == nullptr) {   // one column vector per lane (H <= 128 at VEC 4), no edge_agg
+                                                         // output: the pair fits 64 registers
+      const unsigned grid = persistent_grid(num_edges / 2, kThreads / sh.g, 4);
+      cudaStream_t st = (cudaStream_t)stream;
+#define DMP_PAIR_G(V)                                                                       \
+      do {                                                                                  \
+        if (sh.g == 8) edge_update_pair_kernel<V, 8, 1><<<grid, kThreads, 0, st>>>(p);        \
+        else if (sh.g == 16) edge_update_pair_kernel<V, 16, 1><<<grid, kThreads, 0, st>>>(p); \
+        else edge_update_pair_kernel<V, 32, 1><<<grid, kThreads, 0, st>>>(p);                 \
+      } while (0)
+      if (vec == 4) DMP_PAIR_G(4);
+      else if (vec == 2) DMP_PAIR_G(2);
+      else DMP_PAIR_G(1);
+#undef DMP_PAIR_G
+    } else {
+      DMP_DISPATCH_SHAPE(edge_update_kernel, p, num_edges, (cudaStream_t)stream);
+    }
     int rc = launch_status("edge_update_kernel");
     if (rc != DMP_OK) return rc;
   }

@@ -57,6 +57,8 @@ def edge_update(plan, S, P, Qd, Qs, ebias, order, out=None, edge_agg=None):
         _, ld_agg = _lib.row_major(edge_agg)
     if ebias is not None:
         ebias = ebias.contiguous()
+    if plan.mirrored_halves:
+        order |= _lib.EDGE_MIRRORED_HALVES
     _lib.call("dmp_edge_update", S.device,
               _lib.ptr(plan.a32), _lib.ptr(plan.b32), _lib.ptr(plan.coef), _lib.ptr(S), ldS, _lib.ptr(P), ldP,
               _lib.ptr(Qd), ldQd, _lib.ptr(Qs), ldQs, _lib.ptr(ebias), _lib.ptr(out), ld_out,

@@ -99,7 +99,19 @@ class DMPPlan:
                 self.rev_layout = "halves"
                 self.rev_split = st[1] - 1
         self._norm_perm = {}
+        self._mirrored = None
         del ws
+
+    @property
+    def mirrored_halves(self):
+        """True when edge e + E/2 is the reverse of edge e for every e (one graph after the reversed-edge append,
+        train.py:299-327): both rows then gather the same endpoint rows and `dmp_edge_update` fetches them once.
+        Decided once per plan with two device-side comparisons (one small D2H read)."""
+        if self._mirrored is None:
+            h = self.rev_split
+            self._mirrored = bool(self.rev_layout == "halves" and self.E > 0 and 2 * h == self.E
+                                  and torch.equal(self.a32[:h], self.a32[h:]) and torch.equal(self.b32[:h], self.b32[h:]))
+        return self._mirrored
 
     def norm_permuted(self, norm):
         """`norm` ([E] or [E,1]) re-ordered to CSC position order, cached per tensor version."""

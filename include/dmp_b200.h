@@ -58,6 +58,10 @@ extern "C" {
 /* dmp_edge_update order */
 #define DMP_ORDER_SCM 0 /* ((eloop + add) + agg) + ebias   dmpnn.py:147-149  */
 #define DMP_ORDER_UNC 1 /* ((eloop + agg) + add) + ebias   model.py:257-259  */
+#define DMP_EDGE_MIRRORED_HALVES 16 /* OR-ed into `order`: hint that edge e + E/2 is the reverse of edge e (one graph after
+                                       the reversed-edge append, train.py:299-327), so both gather the same Q_d / Q_s rows:
+                                       the pair is processed together and the rows are fetched once.  Results are
+                                       identical with or without the hint (pairs whose endpoints differ fall back). */
 
 /* activation ids for the fused epilogues (dmpnn.py:138,154 when num_mlp_layers == 0) */
 #define DMP_ACT_NONE 0

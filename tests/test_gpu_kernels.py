@@ -76,6 +76,39 @@ def test_edge_update_bit_exact(n, e0, H, order):
     assert torch.equal(Sg.cpu(), sc.edge_update(cp["a32"], cp["b32"], cp["coef"], S, P, Qd, Qs, None, order))
 
 
+@pytest.mark.parametrize("n,e0,H", SHAPES)
+@pytest.mark.parametrize("order", [0, 1])
+def test_edge_update_mirrored_halves_bit_exact(n, e0, H, order):
+    """[forward | reversed] layout of one graph: edge e + E/2 mirrors edge e, the kernel handles the pair together and
+    fetches the two endpoint rows once (DMP_EDGE_MIRRORED_HALVES).  Same bits as the oracle; a plan whose halves do NOT
+    mirror each other (second half permuted) must not take the hint, and the raw hint on such data still is correct."""
+    from dualmessagepassing_b200 import _lib, functional as F
+    s, d, r = make_graph(seed=3 * n + H, n=n, e0=e0, rev="halves")
+    E = len(s)
+    g = torch.Generator().manual_seed(H + order)
+    S, P = torch.randn(E, H, generator=g), torch.randn(E, H, generator=g)
+    Qd, Qs, eb = torch.randn(n, H, generator=g), torch.randn(n, H, generator=g), torch.randn(H, generator=g)
+    plan = _plan(s, d, n, r)
+    assert plan.rev_layout == "halves" and plan.mirrored_halves
+    cp = _cpu_plan(plan)
+    want = sc.edge_update(cp["a32"], cp["b32"], cp["coef"], S, P, Qd, Qs, eb, order)
+    got = F.edge_update(plan, S.cuda(), P.cuda(), Qd.cuda(), Qs.cuda(), eb.cuda(), order)
+    assert torch.equal(got.cpu(), want)
+    Sg = S.cuda()                                                    # in place over S
+    F.edge_update(plan, Sg, P.cuda(), Qd.cuda(), Qs.cuda(), eb.cuda(), order, out=Sg)
+    assert torch.equal(Sg.cpu(), want)
+    # halves that are not mirrors of each other
+    h = E // 2
+    perm = np.concatenate([np.arange(h), h + np.random.Generator(np.random.PCG64(n)).permutation(h)])
+    plan2 = _plan(s[perm], d[perm], n, r[perm])
+    assert plan2.rev_layout == "halves" and not plan2.mirrored_halves
+    cp2 = _cpu_plan(plan2)
+    want2 = sc.edge_update(cp2["a32"], cp2["b32"], cp2["coef"], S, P, Qd, Qs, eb, order)
+    assert torch.equal(F.edge_update(plan2, S.cuda(), P.cuda(), Qd.cuda(), Qs.cuda(), eb.cuda(), order).cpu(), want2)
+    plan2._mirrored = True                                           # force the hint onto non-mirrored data
+    assert torch.equal(F.edge_update(plan2, S.cuda(), P.cuda(), Qd.cuda(), Qs.cuda(), eb.cuda(), order).cpu(), want2)
+
+
 @pytest.mark.parametrize("n,e0,H", SHAPES[:8])
 def test_edge_backward_bit_exact(n, e0, H):
     from dualmessagepassing_b200 import functional as F
