@@ -6,8 +6,8 @@
 // exactly one float4 per lane of a full warp; narrower rows pack several segments per warp).  A lane
 // owns ITER column vectors and walks the segment's edge list in ascending position, keeping U rows
 // in flight (U independent 128-bit loads per lane) and adding them in order with __fadd_rn, so the
-// result equals a sequential CPU loop bit for bit.  The edge-id list is read with warp-broadcast
-// loads (one 32-bit word per group per edge); bit 31 of each entry is the reversed flag, so neither
+// result equals a sequential CPU loop bit for bit.  The edge-id list is read G entries at a time with one
+// coalesced load per group and broadcast by shuffle; bit 31 of each entry is the reversed flag, so neither
 // the flag nor the sign needs a second gather.
 #include "common.cuh"
 
@@ -34,7 +34,7 @@ struct SegParams {
 // KIND: 0 plain, 1 FILTER (keep only forward / only reversed edges), 2 SPLIT (two sums per segment: forward edges into
 // out[:, 0:H], reversed edges into out[:, H:2H] -- the aggregate-first form of the node update reads every row once)
 template <int VEC, int G, int ITER, int U, int KIND>
-__global__ void __launch_bounds__(kThreads) segment_reduce_kernel(const SegParams p) {
+__global__ void __launch_bounds__(kThreads, 3) segment_reduce_kernel(const SegParams p) {
   constexpr int kGroups = kThreads / G;
   constexpr bool FILTER = (KIND == 1), SPLIT = (KIND == 2);
   const int lane = threadIdx.x % G;
@@ -65,45 +65,53 @@ __global__ void __launch_bounds__(kThreads) segment_reduce_kernel(const SegParam
       if (SPLIT) acc_rev[it][k] = 0.0f;
     }
 
-  for (int j = beg; j < end; j += U) {
-    uint32_t ef[U];
-    float w[U];
+  // The segment's (edge id | flag) words and weights are fetched G at a time with ONE coalesced load per group and
+  // handed out by shuffle: the row addresses of a whole chunk are known up front, so no row load ever waits behind a
+  // dependent index load (was: one broadcast index load per U rows in the critical path of every iteration).
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x % 32) / G * G));
+  for (int j0 = beg; j0 < end; j0 += G) {
+    const int cnt = (end - j0 < G) ? (end - j0) : G;
+    const uint32_t my_ef = lane < cnt ? __ldg(p.eid + j0 + lane) : 0u;
+    const float my_w = (has_w && lane < cnt) ? __ldg(p.w_perm + j0 + lane) : 1.0f;
+    for (int j = 0; j < cnt; j += U) {
+      uint32_t ef[U];
+      float w[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const bool valid = j + u < end;
-      ef[u] = valid ? __ldg(p.eid + j + u) : 0u;
-      w[u] = (valid && has_w) ? __ldg(p.w_perm + j + u) : 1.0f;
-    }
-    Row<VEC> v[U][ITER];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      bool keep = j + u < end;
-      if constexpr (FILTER) {
-        keep = keep && !((filt & DMP_SEG_ONLY_FWD) && (ef[u] >> 31)) && !((filt & DMP_SEG_ONLY_REV) && !(ef[u] >> 31));
-        if (!keep) ef[u] = 0xffffffffu;   // sentinel: (id mask, rev) can never both be all-ones for a real edge
+      for (int u = 0; u < U; ++u) {
+        ef[u] = __shfl_sync(gmask, my_ef, (j + u) & (G - 1), G);
+        w[u] = __shfl_sync(gmask, my_w, (j + u) & (G - 1), G);
       }
-      if (keep) {
-        const uint32_t r = ef[u] >> 31;
-        const float* row = p.V + (int64_t)(ef[u] & DMP_EID_MASK) * p.ldV + (r ? p.rev_off : 0);
+      Row<VEC> v[U][ITER];
 #pragma unroll
-        for (int it = 0; it < ITER; ++it)
-          if (ok[it]) v[u][it] = ld_stream<VEC>(row + col[it]);
+      for (int u = 0; u < U; ++u) {
+        bool keep = j + u < cnt;
+        if constexpr (FILTER) {
+          keep = keep && !((filt & DMP_SEG_ONLY_FWD) && (ef[u] >> 31)) && !((filt & DMP_SEG_ONLY_REV) && !(ef[u] >> 31));
+          if (!keep) ef[u] = 0xffffffffu;   // sentinel: (id mask, rev) can never both be all-ones for a real edge
+        }
+        if (keep) {
+          const uint32_t r = ef[u] >> 31;
+          const float* row = p.V + (int64_t)(ef[u] & DMP_EID_MASK) * p.ldV + (r ? p.rev_off : 0);
+#pragma unroll
+          for (int it = 0; it < ITER; ++it)
+            if (ok[it]) v[u][it] = ld_stream<VEC>(row + col[it]);
+        }
       }
-    }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (j + u < end && (!FILTER || ef[u] != 0xffffffffu)) {
-        const bool neg = sign_by_rev && (ef[u] >> 31) == 0;
+      for (int u = 0; u < U; ++u) {
+        if (j + u < cnt && (!FILTER || ef[u] != 0xffffffffu)) {
+          const bool neg = sign_by_rev && (ef[u] >> 31) == 0;
 #pragma unroll
-        for (int it = 0; it < ITER; ++it) {
-          if (ok[it]) {
+          for (int it = 0; it < ITER; ++it) {
+            if (ok[it]) {
 #pragma unroll
-            for (int k = 0; k < VEC; ++k) {
-              float t = v[u][it].v[k];
-              if (neg) t = -t;
-              if (has_w) t = __fmul_rn(t, w[u]);
-              if (SPLIT && (ef[u] >> 31)) acc_rev[it][k] = __fadd_rn(acc_rev[it][k], t);
-              else acc[it][k] = __fadd_rn(acc[it][k], t);
+              for (int k = 0; k < VEC; ++k) {
+                float t = v[u][it].v[k];
+                if (neg) t = -t;
+                if (has_w) t = __fmul_rn(t, w[u]);
+                if (SPLIT && (ef[u] >> 31)) acc_rev[it][k] = __fadd_rn(acc_rev[it][k], t);
+                else acc[it][k] = __fadd_rn(acc[it][k], t);
+              }
             }
           }
         }

@@ -6,6 +6,6 @@ DMP_B200_LIB=$PWD/$lib timeout 300 python bench.py --no-cpu-baseline --no-e2e --
 import sys,json
 j=json.loads(sys.stdin.read())
 ks=j['kernels']
-print('$lib', round(j['ms_per_step'],1), ' '.join('%s=%.2f' % (k.replace('gemm_tf32x3.','').replace('gemm_',''), v['avg_ms']) for k,v in ks.items() if 'gemm' in k and '@E' in k))
+print('$lib', round(j['ms_per_step'],1), ' '.join('%s=%.2f' % (k.replace('gemm_tf32x3.','').replace('gemm_','').replace('segment_reduce.',''), v['avg_ms']) for k,v in ks.items() if '@N' not in k))
 "
 done; done
