@@ -86,18 +86,21 @@ LAUNCHES = 0     # number of C-ABI kernel-launching calls made so far (bench.py 
 def call(name, device, *args, tag=None, nbytes=None):
     """Invoke one entry point on `device`'s current stream; raise on a non-zero status."""
     global LAUNCHES
-    lib = load()
-    with torch.cuda.device(device):
-        if PROFILE is not None:
+    fn = getattr(load(), name)
+    if PROFILE is not None:
+        with torch.cuda.device(device):
             stream = torch.cuda.current_stream(device)
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            rc = getattr(lib, name)(*args)
+            rc = fn(*args)
             e1.record(stream)
             PROFILE.append((tag or name, e0, e1, nbytes))
-        else:
-            rc = getattr(lib, name)(*args)
+    elif device.index is None or device.index == torch.cuda.current_device():
+        rc = fn(*args)          # common case: no device switch (the guard costs more than the launch on small graphs)
+    else:
+        with torch.cuda.device(device):
+            rc = fn(*args)
     LAUNCHES += 1
     check(rc, name)
 
