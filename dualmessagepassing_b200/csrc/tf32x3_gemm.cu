@@ -21,6 +21,10 @@
 //                           floats of one output row (one 128-byte wavefront per store instead of 32)
 // The weight matrix (<= 64 KB) is split once per CTA and stays resident in smem; accumulators are double
 // buffered in TMEM (2 x N columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <stdlib.h>
+#include <string.h>
+#include <cuda.h>   // CUtensorMap (the encoder is fetched through cudaGetDriverEntryPoint: no libcuda link)
+
 #include "tc_common.cuh"
 
 namespace dmp {
@@ -33,6 +37,7 @@ constexpr int kProducerThreads = kProducerWarps * 32;
 constexpr int kEpilogueWarps = 8;        // two warps per TMEM lane quadrant, each takes half of the columns
 constexpr int kMmaWarp = 8;
 constexpr int kThreadsGemm = (kEpilogueWarps + 1 + kProducerWarps) * 32;  // 544
+constexpr bool kTmaDefault = true;      // streamed operand by TMA unless DMP_GEMM_TMA says otherwise
 constexpr int kPrefetch = 3;            // k-blocks of global loads kept in flight per producer thread
 
 // epilogue flags (low 4 bits = DMP_ACT_*)
@@ -55,6 +60,8 @@ __device__ __forceinline__ uint32_t swz(int r, int c16) { return (uint32_t)(r * 
 struct GemmParams {
   const float* A; int64_t lda;
   const float* row_scale;
+  int use_tma;              // N == 128: the streamed operand arrives by TMA (one cp.async.bulk.tensor per k-block) instead
+                            // of 1 024 per-thread cp.async
   const float* epi_scale;   // accumulate mode, N == 128: the row scale is applied to the ACCUMULATOR (D += s_r * acc_r)
                             // instead of to the streamed operand -- same product, and the producers keep their fast path
   const float* Bt; int64_t ldb;
@@ -115,7 +122,8 @@ __device__ __forceinline__ float epilogue_op(float acc, float bias, float aux, f
 }
 
 template <int N, int K, int MODE>
-__global__ void __launch_bounds__(kThreadsGemm, 1) tf32x3_gemm_kernel(const GemmParams p) {
+__global__ void __launch_bounds__(kThreadsGemm, 1) tf32x3_gemm_kernel(const GemmParams p,
+                                                                      const __grid_constant__ CUtensorMap tmap) {
   using L = Smem<N, K>;
   constexpr int kKBlocks = L::kKBlocks;
   constexpr int kStages = L::kNumStages;
@@ -130,6 +138,7 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) tf32x3_gemm_kernel(const Gemm
   const uint32_t bar_acc_full = sBar + 16 * kStages;         // 2 x 8 B
   const uint32_t bar_acc_empty = bar_acc_full + 16;
   const uint32_t tmem_slot = bar_acc_empty + 16;
+  const uint32_t bar_raw = tmem_slot + 8;                    // kStages x 8 B: TMA completion of the raw (hi) tile
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5;
@@ -147,6 +156,7 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) tf32x3_gemm_kernel(const Gemm
     for (int s = 0; s < kStages; ++s) {
       mbar_init(bar_full + 8 * s, kProducerWarps);        // one arrival per producer warp
       mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_raw + 8 * s, 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_acc_full + 8 * a, 1);
@@ -233,7 +243,14 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) tf32x3_gemm_kernel(const Gemm
       auto issue = [&](int64_t) {
         MBAR_WAIT(bar_empty + 8 * istage, iphase ^ 1);
         const uint32_t hi = sA + istage * L::kStageBytes;
-        if (irow0 + kTileM <= p.M) {
+        if (p.use_tma) {
+          // one elected thread: expected bytes on the stage's mbarrier, then ONE bulk tensor copy of the 128 x 32 box
+          // (rows past M are zero-filled by the TMA unit, the 128-byte swizzle is applied by it too)
+          if (pt == 0) {
+            mbar_expect_tx(bar_raw + 8 * istage, L::kABlockBytes);
+            tma_load_2d(hi, &tmap, ikb * kKB, (int)irow0, bar_raw + 8 * istage);
+          }
+        } else if (irow0 + kTileM <= p.M) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) cp_async16(hi + offs[i], asrc + i * lda32, 16u);
         } else {
@@ -274,9 +291,11 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) tf32x3_gemm_kernel(const Gemm
         cp_async_commit();
       }
       int stage = 0;
+      uint32_t rphase = 0;
       for (int64_t it = 0; it < total_kb; ++it) {
         if (kUseL2Prefetch && it % kKBlocks == 0) l2_prefetch_tile(it / kKBlocks + kL2Ahead + 1);
-        cp_async_wait<kCopyDepth - 1>();                      // this thread's copies of k-block `it` have landed
+        if (p.use_tma) MBAR_WAIT(bar_raw + 8 * stage, rphase);   // the bulk copy of k-block `it` has landed
+        else cp_async_wait<kCopyDepth - 1>();                 // this thread's copies of k-block `it` have landed
         const uint32_t hi = sA + stage * L::kStageBytes;
         const uint32_t lo = hi + L::kABlockBytes;
         if (p.row_scale != nullptr) {
@@ -301,7 +320,7 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) tf32x3_gemm_kernel(const Gemm
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_full + 8 * stage);
-        if (++stage == kStages) stage = 0;
+        if (++stage == kStages) { stage = 0; rphase ^= 1; }
         if (it + kCopyDepth < total_kb) issue(it + kCopyDepth);
         cp_async_commit();
       }
@@ -710,6 +729,38 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) tf32x3_gemm_kernel(const Gemm
   if (warp == kMmaWarp) tmem_dealloc(tmem_base, kTmemCols);
 }
 
+// ---- TMA descriptor of the streamed operand: fp32 [M rows x K], row stride lda, box = 128 rows x 32 floats (one k-block of
+// one tile), 128-byte swizzle = exactly the K-major smem layout the MMA descriptors expect (make_smem_desc / swz()).
+typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TmapEncodeFn tmap_encoder() {
+  static TmapEncodeFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return (TmapEncodeFn)f;
+  }();
+  return fn;
+}
+static bool tma_enabled() {   // DMP_GEMM_TMA=0 switches back to the per-thread cp.async producer (A/B, debugging)
+  static const bool on = [] { const char* e = getenv("DMP_GEMM_TMA"); return e ? atoi(e) != 0 : kTmaDefault; }();
+  return on;
+}
+static bool make_tmap_rows(CUtensorMap* tmap, const float* A, int64_t lda, int64_t M, int K) {
+  TmapEncodeFn enc = tmap_encoder();
+  if (enc == nullptr || M > 0x7fffffffLL) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)M};
+  const cuuint64_t strides[1] = {(cuuint64_t)lda * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)kKB, (cuuint32_t)kTileM};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(A), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int N, int K, int MODE>
 static int launch_gemm_mode(const GemmParams& p, cudaStream_t stream) {
   using L = Smem<N, K>;
@@ -724,7 +775,11 @@ static int launch_gemm_mode(const GemmParams& p, cudaStream_t stream) {
   }
   const int64_t tiles = (p.M + kTileM - 1) / kTileM;
   const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
-  tf32x3_gemm_kernel<N, K, MODE><<<grid, kThreadsGemm, L::kTotal, stream>>>(p);
+  GemmParams q = p;
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  q.use_tma = (L::kTS && tma_enabled() && p.M >= kTileM && make_tmap_rows(&tmap, p.A, p.lda, p.M, K)) ? 1 : 0;
+  tf32x3_gemm_kernel<N, K, MODE><<<grid, kThreadsGemm, L::kTotal, stream>>>(q, tmap);
   return launch_status("tf32x3_gemm_kernel");
 }
 
