@@ -148,3 +148,32 @@ def test_partitioned_algorithm_equals_single_graph_oracle():
             # weight gradients are fp32 sums over all edges, split differently across ranks
             torch.testing.assert_close(g, P[k].grad, rtol=1e-4, atol=1e-5 * max(1.0, float(P[k].grad.abs().max())),
                                        msg=lambda m: k + m)
+
+
+def test_partitioned_split_aggregation_is_local_and_bit_identical():
+    """Aggregate-first node update under the destination-range partition: every rank reduces only the edges it owns
+    (global edge-id order kept) and gets exactly the rows [n_lo, n_hi) of the single-graph [A_fwd | A_rev] sums."""
+    from dualmessagepassing_b200.parallel import partition_by_destination
+    from oracle import sparse_core as sc
+    n, H, world = 203, 24, 4
+    s, d, r = make_graph(seed=31, n=n, e0=1500, rev="halves")
+    E = len(s)
+    g = torch.Generator().manual_seed(1)
+    X, norm = torch.randn(E, H, generator=g), torch.rand(E, generator=g)
+    r8 = torch.from_numpy(r.astype(np.uint8))
+    indptr, eid = sc.stable_segments(torch.from_numpy(d.astype(np.int32)), r8, n)
+    want = sc.seg_reduce(indptr, eid, X, H, w_perm=norm[(eid.long() & 0x7FFFFFFF)], mode=1 | 16)
+    seen = 0
+    for rank in range(world):
+        part = partition_by_destination(s, d, r, n, rank, world)
+        ids = torch.from_numpy(part["eids"])
+        npad = part["num_nodes_padded"]
+        lp, le = sc.stable_segments(torch.from_numpy(part["dst"].astype(np.int32)),
+                                    torch.from_numpy(part["rev"].astype(np.uint8)), npad)
+        lw = norm[ids][(le.long() & 0x7FFFFFFF)]
+        got = sc.seg_reduce(lp, le, X[ids], H, w_perm=lw, mode=1 | 16)
+        lo, hi = part["n_lo"], min(part["n_hi"], n)
+        assert torch.equal(got[lo:hi], want[lo:hi])
+        assert float(got[:lo].abs().sum()) == 0 and float(got[part["n_hi"]:].abs().sum()) == 0
+        seen += ids.numel()
+    assert seen == E
