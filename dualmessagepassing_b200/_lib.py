@@ -26,6 +26,7 @@ ACT_NONE, ACT_RELU, ACT_LEAKY_RELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3, 4
 ACT_FROM_OUTPUT = 16
 EPI_MUL_ACT_GRAD = 32
 EPI_ACCUMULATE = 64
+DUAL_STORE, DUAL_ACCUMULATE, DUAL_SEPARATE = 0, 1, 2
 
 _vp, _i64, _i32, _f32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_float
 
@@ -47,6 +48,11 @@ SIGNATURES = {
     "dmp_gemm_tn_workspace_bytes": [_i64, _i64, ctypes.POINTER(ctypes.c_int64)],
     "dmp_gemm_tn_tf32x3": [_vp, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _i32, _vp, _i64, _vp],
     "dmp_gemm_tf32x3": [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _i32, _f32, _vp],
+    "dmp_gemm_tf32x3_dual": [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _i32, _vp],
+    "dmp_bn_workspace_bytes": [_i64, ctypes.POINTER(ctypes.c_int64)],
+    "dmp_bn_stats": [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _vp],
+    "dmp_bn_act": [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _f32, _vp],
+    "dmp_bn_backward": [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _i32, _vp, _i64, _vp],
 }
 
 _lib = None

@@ -56,7 +56,8 @@ __global__ void __launch_bounds__(kThreads) edge_update_kernel(const EdgeFwdPara
     const int b = __ldg(p.b32 + e);
     const float c = __ldg(p.coef + e);
     const float* s_row = p.S + e * p.ldS;
-    const float* p_row = p.P + e * p.ldP;
+    const bool has_p = p.P != nullptr;   // NULL: S already holds eloop + coef*P (fused dual projection, SCM order)
+    const float* p_row = has_p ? p.P + e * p.ldP : nullptr;
     const float* qd_row = p.Qd + (int64_t)a * p.ldQd;
     const float* qs_row = p.Qs + (int64_t)b * p.ldQs;
     Row<VEC> s[ITER], pp[ITER], qd[ITER], qs[ITER];
@@ -66,7 +67,7 @@ __global__ void __launch_bounds__(kThreads) edge_update_kernel(const EdgeFwdPara
         qd[it] = ld_row<VEC>(qd_row + col[it]);
         qs[it] = ld_row<VEC>(qs_row + col[it]);
         s[it] = ld_plain<VEC>(s_row + col[it]);  // may alias out
-        pp[it] = ld_stream<VEC>(p_row + col[it]);
+        if (has_p) pp[it] = ld_stream<VEC>(p_row + col[it]);
       }
     }
 #pragma unroll
@@ -76,10 +77,14 @@ __global__ void __launch_bounds__(kThreads) edge_update_kernel(const EdgeFwdPara
 #pragma unroll
       for (int k = 0; k < VEC; ++k) {
         const float msg = __fsub_rn(qd[it].v[k], qs[it].v[k]);
-        const float add = __fmul_rn(c, pp[it].v[k]);
         float t;
-        if (p.order == DMP_ORDER_SCM) t = __fadd_rn(__fadd_rn(s[it].v[k], add), msg);
-        else t = __fadd_rn(__fadd_rn(s[it].v[k], msg), add);
+        if (!has_p) {
+          t = __fadd_rn(s[it].v[k], msg);
+        } else {
+          const float add = __fmul_rn(c, pp[it].v[k]);
+          if (p.order == DMP_ORDER_SCM) t = __fadd_rn(__fadd_rn(s[it].v[k], add), msg);
+          else t = __fadd_rn(__fadd_rn(s[it].v[k], msg), add);
+        }
         if (p.ebias != nullptr) t = __fadd_rn(t, bias[it].v[k]);
         o.v[k] = t;
         m.v[k] = msg;
@@ -100,6 +105,7 @@ __global__ void __launch_bounds__(kThreads, 4) edge_update_pair_kernel(const Edg
   const int lane = threadIdx.x % G;
   const int64_t stride = (int64_t)gridDim.x * kGroups;
   const int64_t half = p.E / 2;
+  const bool has_p = p.P != nullptr;
   int col[ITER];
   bool ok[ITER];
   Row<VEC> bias[ITER];
@@ -124,9 +130,11 @@ __global__ void __launch_bounds__(kThreads, 4) edge_update_pair_kernel(const Edg
         qd[it] = ld_row<VEC>(qd_row + col[it]);
         qs[it] = ld_row<VEC>(qs_row + col[it]);
         s[it] = ld_plain<VEC>(p.S + e * p.ldS + col[it]);     // may alias out
-        pp[it] = ld_stream<VEC>(p.P + e * p.ldP + col[it]);
         s2[it] = ld_plain<VEC>(p.S + e2 * p.ldS + col[it]);
-        pp2[it] = ld_stream<VEC>(p.P + e2 * p.ldP + col[it]);
+        if (has_p) {
+          pp[it] = ld_stream<VEC>(p.P + e * p.ldP + col[it]);
+          pp2[it] = ld_stream<VEC>(p.P + e2 * p.ldP + col[it]);
+        }
       }
     }
     auto emit = [&](int64_t row, float cc, const Row<VEC> (&sv)[ITER], const Row<VEC> (&pv)[ITER]) {
@@ -137,10 +145,14 @@ __global__ void __launch_bounds__(kThreads, 4) edge_update_pair_kernel(const Edg
 #pragma unroll
         for (int k = 0; k < VEC; ++k) {
           const float msg = __fsub_rn(qd[it].v[k], qs[it].v[k]);
-          const float add = __fmul_rn(cc, pv[it].v[k]);
           float t;
-          if (p.order == DMP_ORDER_SCM) t = __fadd_rn(__fadd_rn(sv[it].v[k], add), msg);
-          else t = __fadd_rn(__fadd_rn(sv[it].v[k], msg), add);
+          if (!has_p) {
+            t = __fadd_rn(sv[it].v[k], msg);
+          } else {
+            const float add = __fmul_rn(cc, pv[it].v[k]);
+            if (p.order == DMP_ORDER_SCM) t = __fadd_rn(__fadd_rn(sv[it].v[k], add), msg);
+            else t = __fadd_rn(__fadd_rn(sv[it].v[k], msg), add);
+          }
           if (p.ebias != nullptr) t = __fadd_rn(t, bias[it].v[k]);
           o.v[k] = t;
         }
@@ -337,20 +349,20 @@ extern "C" int dmp_edge_update(const int32_t* a32, const int32_t* b32, const flo
   using namespace dmp;
   DMP_CHECK_ARG(num_edges >= 0 && H >= 0, "edge_update: negative size");
   if (num_edges == 0 || H == 0) return DMP_OK;
-  DMP_CHECK_ARG(a32 && b32 && coef && S && P && Qd && Qs && out, "edge_update: null pointer");
+  DMP_CHECK_ARG(a32 && b32 && coef && S && Qd && Qs && out, "edge_update: null pointer");   // P may be NULL
   const bool pair = (order & DMP_EDGE_MIRRORED_HALVES) != 0 && num_edges % 2 == 0;
   order &= ~DMP_EDGE_MIRRORED_HALVES;
   DMP_CHECK_ARG(order == DMP_ORDER_SCM || order == DMP_ORDER_UNC, "edge_update: bad order %d", order);
-  DMP_CHECK_ARG(ldS >= H && ldP >= H && ldQd >= H && ldQs >= H && ld_out >= H && (!edge_agg || ld_agg >= H),
+  DMP_CHECK_ARG(ldS >= H && (!P || ldP >= H) && ldQd >= H && ldQs >= H && ld_out >= H && (!edge_agg || ld_agg >= H),
                 "edge_update: leading dimension smaller than H");
-  DMP_CHECK_ARG(P != out && Qd != out && Qs != out, "edge_update: only S may alias out");
-  const int vec = pick_vec(H, {ldS, ldP, ldQd, ldQs, ld_out, edge_agg ? ld_agg : 0},
+  DMP_CHECK_ARG((P == nullptr || P != out) && Qd != out && Qs != out, "edge_update: only S may alias out");
+  const int vec = pick_vec(H, {ldS, P ? ldP : 0, ldQd, ldQs, ld_out, edge_agg ? ld_agg : 0},
                            {S, P, Qd, Qs, ebias, out, edge_agg});
   const int64_t chunk = max_chunk(vec);
   for (int64_t c0 = 0; c0 < H; c0 += chunk) {
     EdgeFwdParams p;
     p.a32 = a32; p.b32 = b32; p.coef = coef;
-    p.S = S + c0; p.ldS = ldS; p.P = P + c0; p.ldP = ldP;
+    p.S = S + c0; p.ldS = ldS; p.P = P ? P + c0 : nullptr; p.ldP = ldP;
     p.Qd = Qd + c0; p.ldQd = ldQd; p.Qs = Qs + c0; p.ldQs = ldQs;
     p.ebias = ebias ? ebias + c0 : nullptr;
     p.out = out + c0; p.ld_out = ld_out;

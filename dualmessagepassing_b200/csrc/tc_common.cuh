@@ -1,5 +1,9 @@
 // tc_common.cuh -- PTX wrappers shared by the tcgen05 kernels (mbarrier, proxy fences, TMEM, tcgen05.mma/ld/commit).
 #pragma once
+#include <stdlib.h>
+#include <string.h>
+#include <cuda.h>   // CUtensorMap (the encoder is fetched through cudaGetDriverEntryPoint: no libcuda link)
+
 #include "common.cuh"
 
 namespace dmp {
@@ -177,6 +181,58 @@ __device__ __forceinline__ void split_store(uint32_t hi_addr, uint32_t lo_addr, 
   asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(hi_addr), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
   asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(lo_addr), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
 }
+
+
+// ---- shared by the row-streaming kernels (tf32x3_gemm.cu, tf32x3_gemm_dual.cu) ----------------------------------
+constexpr int kTileM = 128;
+constexpr int kKB = 32;                 // fp32 elements per k-block = one 128-byte swizzle row
+
+// K-major, 128-byte swizzle: rows of 128 B, 8-row groups of 1024 B (SBO), descriptor version 1 (sm_100)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// kind::tf32, fp32 accumulate, A and B K-major, M = 128
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// byte offset of 16-byte chunk `c16` of row `r` inside a [rows x 128 B] swizzled block
+__device__ __forceinline__ uint32_t swz(int r, int c16) { return (uint32_t)(r * 128 + ((c16 ^ (r & 7)) << 4)); }
+
+
+// ---- TMA descriptor of the streamed operand: fp32 [M rows x K], row stride lda, box = 128 rows x 32 floats (one k-block of
+// one tile), 128-byte swizzle = exactly the K-major smem layout the MMA descriptors expect (make_smem_desc / swz()).
+typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline TmapEncodeFn tmap_encoder() {
+  static TmapEncodeFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return (TmapEncodeFn)f;
+  }();
+  return fn;
+}
+inline bool tma_enabled() {   // DMP_GEMM_TMA=0 switches back to the per-thread cp.async producer (A/B, debugging)
+  static const bool on = [] { const char* e = getenv("DMP_GEMM_TMA"); return e ? atoi(e) != 0 : true; }();
+  return on;
+}
+inline bool make_tmap_rows(CUtensorMap* tmap, const float* A, int64_t lda, int64_t M, int K) {
+  TmapEncodeFn enc = tmap_encoder();
+  if (enc == nullptr || M > 0x7fffffffLL) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)M};
+  const cuuint64_t strides[1] = {(cuuint64_t)lda * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)kKB, (cuuint32_t)kTileM};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(A), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 
 
 }  // namespace gemm

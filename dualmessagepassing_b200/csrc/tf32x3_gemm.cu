@@ -21,17 +21,11 @@
 //                           floats of one output row (one 128-byte wavefront per store instead of 32)
 // The weight matrix (<= 64 KB) is split once per CTA and stays resident in smem; accumulators are double
 // buffered in TMEM (2 x N columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
-#include <stdlib.h>
-#include <string.h>
-#include <cuda.h>   // CUtensorMap (the encoder is fetched through cudaGetDriverEntryPoint: no libcuda link)
-
 #include "tc_common.cuh"
 
 namespace dmp {
 namespace gemm {
 
-constexpr int kTileM = 128;
-constexpr int kKB = 32;                 // fp32 elements per k-block = one 128-byte swizzle row
 constexpr int kProducerWarps = 8;
 constexpr int kProducerThreads = kProducerWarps * 32;
 constexpr int kEpilogueWarps = 8;        // two warps per TMEM lane quadrant, each takes half of the columns
@@ -43,19 +37,6 @@ constexpr int kPrefetch = 3;            // k-blocks of global loads kept in flig
 // epilogue flags (low 4 bits = DMP_ACT_*)
 constexpr int kEpiMulActGradFromOutput = 32;  // D = acc * act'(aux) with aux = activation OUTPUT
 constexpr int kEpiAccumulate = 64;            // D += acc
-
-// K-major, 128-byte swizzle: rows of 128 B, 8-row groups of 1024 B (SBO), descriptor version 1 (sm_100)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
-         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-}
-// kind::tf32, fp32 accumulate, A and B K-major, M = 128
-__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
-
-// byte offset of 16-byte chunk `c16` of row `r` inside a [rows x 128 B] swizzled block
-__device__ __forceinline__ uint32_t swz(int r, int c16) { return (uint32_t)(r * 128 + ((c16 ^ (r & 7)) << 4)); }
 
 struct GemmParams {
   const float* A; int64_t lda;
@@ -144,11 +125,18 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) tf32x3_gemm_kernel(const Gemm
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int64_t num_tiles = (p.M + kTileM - 1) / kTileM;
-  // ablation switches for performance triage (scripts/gemm_ablate.py); all zero in production calls
+  // ablation switches for performance triage (scripts/gemm_ablate.py): compiled in only with -DDMP_DEBUG; the release
+  // library rejects the corresponding epilogue bits (dmp_gemm_tf32x3) and these fold to constants
+#ifdef DMP_DEBUG
   const bool dbg_no_ldg = (p.epilogue >> 8) & 1, dbg_no_sts = (p.epilogue >> 9) & 1;
   const bool dbg_no_mma = (p.epilogue >> 10) & 1, dbg_no_stg = (p.epilogue >> 11) & 1;
   const bool dbg_no_fence = (p.epilogue >> 12) & 1, dbg_spin = (p.epilogue >> 13) & 1, dbg_no_tld = (p.epilogue >> 14) & 1;
   long long* dbg_ts = ((p.epilogue >> 16) & 1) && blockIdx.x == 0 ? (long long*)p.aux : nullptr;  // [3][256][2]
+#else
+  constexpr bool dbg_no_ldg = false, dbg_no_sts = false, dbg_no_mma = false, dbg_no_stg = false, dbg_no_fence = false,
+                 dbg_spin = false, dbg_no_tld = false;
+  constexpr long long* dbg_ts = nullptr;
+#endif
 #define MBAR_WAIT(bar, par) do { if (dbg_spin) mbar_wait_spin(bar, par); else mbar_wait(bar, par); } while (0)
 
   // ---- one-time setup: barriers, TMEM, resident split weights ---------------------------------------------
@@ -729,38 +717,6 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) tf32x3_gemm_kernel(const Gemm
   if (warp == kMmaWarp) tmem_dealloc(tmem_base, kTmemCols);
 }
 
-// ---- TMA descriptor of the streamed operand: fp32 [M rows x K], row stride lda, box = 128 rows x 32 floats (one k-block of
-// one tile), 128-byte swizzle = exactly the K-major smem layout the MMA descriptors expect (make_smem_desc / swz()).
-typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static TmapEncodeFn tmap_encoder() {
-  static TmapEncodeFn fn = [] {
-    void* f = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-      f = nullptr;
-    return (TmapEncodeFn)f;
-  }();
-  return fn;
-}
-static bool tma_enabled() {   // DMP_GEMM_TMA=0 switches back to the per-thread cp.async producer (A/B, debugging)
-  static const bool on = [] { const char* e = getenv("DMP_GEMM_TMA"); return e ? atoi(e) != 0 : kTmaDefault; }();
-  return on;
-}
-static bool make_tmap_rows(CUtensorMap* tmap, const float* A, int64_t lda, int64_t M, int K) {
-  TmapEncodeFn enc = tmap_encoder();
-  if (enc == nullptr || M > 0x7fffffffLL) return false;
-  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)M};
-  const cuuint64_t strides[1] = {(cuuint64_t)lda * 4};
-  const cuuint32_t box[2] = {(cuuint32_t)kKB, (cuuint32_t)kTileM};
-  const cuuint32_t estr[2] = {1, 1};
-  return enc(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(A), dims, strides, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 template <int N, int K, int MODE>
 static int launch_gemm_mode(const GemmParams& p, cudaStream_t stream) {
   using L = Smem<N, K>;
@@ -815,6 +771,10 @@ extern "C" int dmp_gemm_tf32x3(const float* A, int64_t lda, const float* row_sca
                 "gemm_tf32x3: operands must be 16-byte aligned");
   const int act = epilogue & 15;
   DMP_CHECK_ARG(act >= DMP_ACT_NONE && act <= DMP_ACT_SIGMOID, "gemm_tf32x3: bad activation");
+#ifndef DMP_DEBUG
+  DMP_CHECK_ARG((epilogue & ~(15 | kEpiMulActGradFromOutput | kEpiAccumulate)) == 0, "gemm_tf32x3: unknown epilogue bits 0x%x",
+                epilogue);
+#endif
   DMP_CHECK_ARG(!(epilogue & kEpiMulActGradFromOutput) || (aux != nullptr && ld_aux >= N && ld_aux % 4 == 0),
                 "gemm_tf32x3: act' epilogue needs aux");
   DMP_CHECK_ARG(A != D, "gemm_tf32x3: D must not alias A");

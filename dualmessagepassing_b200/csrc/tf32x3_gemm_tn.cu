@@ -490,11 +490,15 @@ extern "C" int dmp_gemm_tn_tf32x3(const float* X, int64_t ldx, const float* row_
   p.part_sg = colsum_g ? p.partial + grid * (M * N + M) : nullptr;
   // 4096 B between 32-feature blocks (LBO), 512 B between 4-edge atoms (SBO), 1024 B per MMA k-step (8 edges)
   p.lbo = kTnEdges * 128; p.sbo = 512; p.kadv = 1024; p.idesc_xor = 0; p.ltype = 1;
-  // debug overrides, read once per process: descriptor geometry (scripts/tn_probe.py) and ablation (scripts/tn_ablate.py)
+  p.ablate = 0;
+#ifdef DMP_DEBUG
+  // debug overrides, read once per process: descriptor geometry (scripts/tn_probe.py) and ablation (scripts/tn_ablate.py);
+  // not compiled into the release library
   static const char* const dbg = getenv("DMP_TN_DBG");
   static const int ablate = getenv("DMP_TN_ABLATE") ? atoi(getenv("DMP_TN_ABLATE")) : 0;
   if (dbg) sscanf(dbg, "%u,%u,%u,%u,%u", &p.lbo, &p.sbo, &p.kadv, &p.idesc_xor, &p.ltype);
   p.ablate = ablate;
+#endif
   cudaStream_t s = (cudaStream_t)stream;
   int rc;
   if (M == 128 && N == 128) rc = launch_tn<128, 128>(p, (unsigned)grid, s);

@@ -43,9 +43,13 @@ def segment_reduce(indptr, eid, V, H, *, w_perm=None, rev_col_offset=0, base=Non
 
 def edge_update(plan, S, P, Qd, Qs, ebias, order, out=None, edge_agg=None):
     """Raw call of dmp_edge_update; `out` may be S itself (in place)."""
+    if S.shape[0] != plan.E or (P is not None and P.shape[0] != plan.E):
+        raise ValueError("edge_update: operands have %d rows, the graph has %d edges" % (S.shape[0], plan.E))
     _lib.require_cuda(S, P, Qd, Qs, ebias)
     S, ldS = _lib.row_major(S)
-    P, ldP = _lib.row_major(P)
+    ldP = 0
+    if P is not None:   # None: S already holds eloop + coef*P (gemm_tf32x3_dual, DUAL_STORE)
+        P, ldP = _lib.row_major(P)
     Qd, ldQd = _lib.row_major(Qd)
     Qs, ldQs = _lib.row_major(Qs)
     E, H = S.shape
@@ -67,8 +71,10 @@ def edge_update(plan, S, P, Qd, Qs, ebias, order, out=None, edge_agg=None):
 
 
 def edge_backward(plan, norm_flat, gN, gE, *, want_T=True, want_CG=True, t_rev_col_offset=0, T=None, CG=None,
-                  gN_rev=None):
-    """Raw call of dmp_edge_backward: T = sgn*gN[dst]*norm (optionally into the rev half), CG = coef*gE."""
+                  gN_rev=None, row_offset=0):
+    """Raw call of dmp_edge_backward: T = sgn*gN[dst]*norm (optionally into the rev half), CG = coef*gE.
+    row_offset: gN / gN_rev hold rows [row_offset, row_offset + gN.shape[0]) of the table the plan's destination ids
+    index (destination-range partition: every local edge's destination is owned, so only the owned slice exists)."""
     H = gN.shape[1] if gN is not None else gE.shape[1]
     dev = gN.device if gN is not None else gE.device
     ld_gN = ld_gE = ldT = ldCG = 0
@@ -91,11 +97,19 @@ def edge_backward(plan, norm_flat, gN, gE, *, want_T=True, want_CG=True, t_rev_c
         _, ldCG = _lib.row_major(CG)
     _lib.call("dmp_edge_backward", dev,
               _lib.ptr(plan.dst32), _lib.ptr(plan.rev), _lib.ptr(norm_flat), _lib.ptr(plan.coef),
-              _lib.ptr(gN if want_T else None), _lib.ptr(gN_rev if want_T else None), ld_gN,
+              _shift(gN if want_T else None, row_offset, ld_gN), _shift(gN_rev if want_T else None, row_offset, ld_gN),
+              ld_gN,
               _lib.ptr(gE if want_CG else None), ld_gE,
               _lib.ptr(T if want_T else None), ldT, t_rev_col_offset, _lib.ptr(CG if want_CG else None), ldCG,
               plan.E, H, _lib.stream_ptr(dev), tag="edge_backward")
     return (T if want_T else None), (CG if want_CG else None)
+
+
+def _shift(t, row_offset, ld):
+    """Device pointer of the (virtual) row 0 of a table whose first stored row is `row_offset`."""
+    if t is None:
+        return None
+    return t.data_ptr() - int(row_offset) * int(ld) * 4
 
 
 class _SparseCore(torch.autograd.Function):
@@ -167,6 +181,10 @@ class _GateResidual(torch.autograd.Function):
         g = None
         if gate is not None:
             g = gate.reshape(-1).contiguous().float()
+            if g.numel() != rows:
+                raise ValueError("gate_residual: gate has %d entries, x has %d rows" % (g.numel(), rows))
+        if prev is not None and tuple(prev.shape) != (rows, H):
+            raise ValueError("gate_residual: prev is %s, x is %s" % (tuple(prev.shape), (rows, H)))
         _lib.call("dmp_gate_residual", x.device, _lib.ptr(x), ldx, _lib.ptr(g), _lib.ptr(prev), ld_prev,
                   _lib.ptr(out), H, rows, H, act, slope, _stream(x), tag="gate_residual")
         ctx.save_for_backward(x if act != _lib.ACT_NONE else None, g)
@@ -192,7 +210,11 @@ class _GateResidual(torch.autograd.Function):
 
 
 def gate_residual(x, gate=None, prev=None, act="none", slope=0.0):
-    """Fused `prev + gate * act(x)`; gate is [rows] or [rows,1] (0/1 mask or soft gate), no grad to it."""
+    """Fused `prev + gate * act(x)`; gate is [rows] or [rows,1] (0/1 mask or soft gate), no grad to it.
+
+    Differences from the reference's torch ops, by construction: a 0 gate MULTIPLIES (0 * NaN = NaN, where
+    `masked_fill` would give 0), and a gate that requires grad is refused (the reference's gates are label-match
+    masks computed without grad, basemodel.py:1394-1423)."""
     if gate is not None and gate.requires_grad:
         raise NotImplementedError("gate_residual does not differentiate with respect to the gate")
     return _GateResidual.apply(x, gate, prev, _ACT_IDS[act], float(slope))
@@ -258,7 +280,7 @@ def gemm_tn_tf32x3(X, G, *, row_scale=None, out=None, accumulate=False, colsum_x
             raise ValueError("accumulate=True needs `out`")
         out = torch.empty((M, N), dtype=torch.float32, device=X.device)
     _, ldd = _lib.row_major(out)
-    key = (str(X.device), M, N)
+    key = (str(X.device), _stream(X), M, N)   # one workspace per stream: concurrent calls must not share partials
     ws = _tn_ws.get(key)
     if ws is None:
         import ctypes
@@ -299,3 +321,98 @@ def gemm_tf32x3_acc_gather(A, Wt, out, *, dst32, tab_fwd, tab_rev=None, rev=None
               _lib.ptr(tab_rev), ld_tab, _stream(A), tag="gemm_tf32x3.acc_gather",
               nbytes=4 * (M * K + 3 * M * N + N * K) + 9 * M)
     return out
+
+
+def gemm_tf32x3_dual(A, W1t, W2t, *, row_scale=None, mode="store", out=None, out2=None):
+    """Two projections of the same streamed operand in ONE pass (dmp_gemm_tf32x3_dual):
+        "store"       out  = A @ W1t.T + row_scale ⊙ (A @ W2t.T)
+        "accumulate"  out  = (out + A @ W1t.T) + row_scale ⊙ (A @ W2t.T)
+        "separate"    out, out2 = A @ W1t.T, A @ W2t.T
+    A [M,K] fp32 dense rows; W1t, W2t [N,K] (nn.Linear layout); N, K in {64,128}.  Raw, non-differentiable."""
+    _lib.require_cuda(A, W1t, W2t, row_scale, out, out2)
+    A, lda = _lib.row_major(A)
+    W = torch.stack([W1t, W2t]).contiguous()       # common leading dimension, 16-byte aligned
+    M, K = A.shape
+    N = W1t.shape[0]
+    if tuple(W1t.shape) != (N, K) or tuple(W2t.shape) != (N, K):
+        raise ValueError("weights must both be [N,K]=[%d,%d]: got %s, %s" % (N, K, tuple(W1t.shape), tuple(W2t.shape)))
+    imode = {"store": _lib.DUAL_STORE, "accumulate": _lib.DUAL_ACCUMULATE, "separate": _lib.DUAL_SEPARATE}[mode]
+    if out is None:
+        if mode == "accumulate":
+            raise ValueError("accumulate needs `out`")
+        out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    _, ldd = _lib.row_major(out)
+    ldd2 = 0
+    if mode == "separate":
+        if out2 is None:
+            out2 = torch.empty((M, N), dtype=torch.float32, device=A.device)
+        _, ldd2 = _lib.row_major(out2)
+    if row_scale is not None:
+        row_scale = row_scale.reshape(-1).contiguous()
+        if row_scale.numel() != M:
+            raise ValueError("row_scale has %d entries for %d rows" % (row_scale.numel(), M))
+    _lib.call("dmp_gemm_tf32x3_dual", A.device, _lib.ptr(A), lda, _lib.ptr(W[0]), _lib.ptr(W[1]), K,
+              _lib.ptr(row_scale), _lib.ptr(out), ldd, _lib.ptr(out2 if mode == "separate" else None), ldd2, M, N, K,
+              imode, _stream(A), tag="gemm_tf32x3_dual." + mode,
+              nbytes=4 * (M * K + M * N * {"store": 1, "accumulate": 2, "separate": 2}[mode] + 2 * N * K)
+              + (4 * M if row_scale is not None else 0))
+    return (out, out2) if mode == "separate" else out
+
+
+_bn_ws = {}
+
+
+def _bn_workspace(device, H):
+    import ctypes
+    key = (str(device), _lib.stream_ptr(device), H)
+    ws = _bn_ws.get(key)
+    if ws is None:
+        nb = ctypes.c_int64(0)
+        _lib.check(_lib.load().dmp_bn_workspace_bytes(H, ctypes.byref(nb)), "dmp_bn_workspace_bytes")
+        ws = _bn_ws[key] = torch.zeros(nb.value, dtype=torch.uint8, device=device)   # zeroed once; kernels keep it so
+    return ws
+
+
+def bn_stats(x):
+    """(mean, biased variance) over the rows of x [rows,H]: two deterministic passes (dmp_bn_stats)."""
+    _lib.require_cuda(x)
+    x, ldx = _lib.row_major(x)
+    rows, H = x.shape
+    mean = torch.empty(H, dtype=torch.float32, device=x.device)
+    var = torch.empty(H, dtype=torch.float32, device=x.device)
+    ws = _bn_workspace(x.device, H)
+    _lib.call("dmp_bn_stats", x.device, _lib.ptr(x), ldx, rows, H, _lib.ptr(mean), _lib.ptr(var), _lib.ptr(ws),
+              ws.numel(), _stream(x), tag="bn_stats", nbytes=2 * 4 * rows * H)
+    return mean, var
+
+
+def bn_act(x, mean, invstd, gamma, beta, act, slope, out=None):
+    """act(((x - mean) * invstd) * gamma + beta), elementwise (dmp_bn_act)."""
+    _lib.require_cuda(x, mean, invstd, gamma, beta)
+    x, ldx = _lib.row_major(x)
+    rows, H = x.shape
+    if out is None:
+        out = torch.empty((rows, H), dtype=torch.float32, device=x.device)
+    _, ldo = _lib.row_major(out)
+    _lib.call("dmp_bn_act", x.device, _lib.ptr(x), ldx, _lib.ptr(mean), _lib.ptr(invstd), _lib.ptr(gamma),
+              _lib.ptr(beta), _lib.ptr(out), ldo, rows, H, act, float(slope), _stream(x), tag="bn_act",
+              nbytes=2 * 4 * rows * H)
+    return out
+
+
+def bn_backward(g, x, mean, invstd, gamma, training, out=None):
+    """(gx, dgamma, dbeta) of y = ((x - mean) * invstd) * gamma + beta given g = dL/dy; gx may be g (in place)."""
+    _lib.require_cuda(g, x, mean, invstd, gamma)
+    g, ldg = _lib.row_major(g)
+    x, ldx = _lib.row_major(x)
+    rows, H = g.shape
+    if out is None:
+        out = g
+    _, ldo = _lib.row_major(out)
+    dgamma = torch.empty(H, dtype=torch.float32, device=g.device)
+    dbeta = torch.empty(H, dtype=torch.float32, device=g.device)
+    ws = _bn_workspace(g.device, H)
+    _lib.call("dmp_bn_backward", g.device, _lib.ptr(g), ldg, _lib.ptr(x), ldx, _lib.ptr(mean), _lib.ptr(invstd),
+              _lib.ptr(gamma), _lib.ptr(out), ldo, _lib.ptr(dgamma), _lib.ptr(dbeta), rows, H, int(bool(training)),
+              _lib.ptr(ws), ws.numel(), _stream(g), tag="bn_backward", nbytes=5 * 4 * rows * H)
+    return out, dgamma, dbeta

@@ -21,7 +21,8 @@ from .act import map_activation_str_to_layer
 from .constants import (EDGEFEAT, LEAKY_RELU_A, NODEFEAT, OUTDEGREE, REVFLAG, UNC_FEAT, UNC_NORM,
                         UNC_OUTDEGREE, UNC_REVFLAG)
 from .functional import sparse_core
-from .fused import fused_dmp_layer, supported_activation
+from . import fused as _fused
+from .fused import fused_dmp_layer, mlp_spec_and_tensors, supported_activation
 from .init import init_module, init_weight
 from .plan import get_plan
 
@@ -82,6 +83,70 @@ def dual_message_passing(plan, node_feat, edge_feat, in_weight, out_weight, src_
         M = X_e @ torch.cat([in_weight, out_weight], dim=1)  # [E, 2H]: branch picked inside the kernel
         m_rev_off = H
     return sparse_core(plan, M, S, P, Ln, Qd, Qs, nbias, ebias, norm=norm, order=order, m_rev_off=m_rev_off)
+
+
+def _padded_width(d):
+    """Width the tcgen05 kernels take (64 or 128) for a feature dimension d, or None when d > 128."""
+    return 64 if d <= 64 else (128 if d <= 128 else None)
+
+
+def _pad_cols(t, width):
+    """Zero-pad the last dimension to `width` (differentiable: autograd slices the gradient back)."""
+    return t if t is None or t.shape[-1] == width else torch.nn.functional.pad(t, (0, width - t.shape[-1]))
+
+
+def _pad_mat(w, rows, cols):
+    return torch.nn.functional.pad(w, (0, cols - w.shape[1], 0, rows - w.shape[0]))
+
+
+def _run_fused(layer, plan, node_feat, edge_feat, nmlp, emlp, *, act_func, slope, order, norm=None, post_act="none"):
+    """Whole-layer function (fused.py) with the widths the tensor-core kernels take.
+
+    UNC/run.sh trains with hidden 50: when the graph is large enough for the tcgen05 kernels and a width is not
+    64 / 128, features, weights, biases and BatchNorm affine parameters are zero-padded to the next supported
+    width (exact: padded inputs meet zero weights, padded outputs are exactly 0 and are sliced off; the gradient of
+    the padding is the slice)."""
+    Din, H = layer.input_dim, layer.hidden_dim
+    weights = (layer.in_weight, layer.out_weight, layer.src_weight, layer.dst_weight, layer.nloop_weight,
+               layer.eloop_weight)
+    nbias, ebias = layer.nbias, layer.ebias
+    pd, ph = _padded_width(Din), _padded_width(H)
+    pad = (_fused.DENSE_BACKEND == "auto" and edge_feat.shape[0] >= _fused.TC_MIN_ROWS and pd is not None
+           and ph is not None and (pd != Din or ph != H))
+    xv, xe = node_feat.float(), edge_feat.float()
+    if pad:
+        weights = tuple(_pad_mat(w, pd, ph) for w in weights)
+        nbias, ebias = _pad_cols(nbias, ph), _pad_cols(ebias, ph)
+
+        def pad_mlp(m):
+            spec, ts = m
+            out = []
+            for t in ts:
+                out.append(None if t is None else (_pad_mat(t, ph, ph) if t.dim() == 2 else _pad_cols(t, ph)))
+            return spec, out
+
+        nmlp, emlp = pad_mlp(nmlp), pad_mlp(emlp)
+        xv, xe = _pad_cols(xv, pd), _pad_cols(xe, pd)
+    nv, ne = fused_dmp_layer(plan, xv, xe, weights, nbias, ebias, nmlp, emlp, act_func=act_func, slope=slope,
+                             order=order, norm=norm, post_act=post_act, training=layer.training)
+    if pad and ph != H:
+        nv, ne = nv[:, :H], ne[:, :H]
+    return nv, ne
+
+
+def _act_of_module(m):
+    """(name, slope) of an activation module the fused kernels implement, else None."""
+    if m is None or isinstance(m, nn.Identity):
+        return "none", 0.0
+    if isinstance(m, nn.LeakyReLU):
+        return "leaky_relu", float(m.negative_slope)
+    if isinstance(m, nn.ReLU):
+        return "relu", 0.0
+    if isinstance(m, nn.Tanh):
+        return "tanh", 0.0
+    if isinstance(m, nn.Sigmoid):
+        return "sigmoid", 0.0
+    return None
 
 
 class DMPLayer(nn.Module):
@@ -149,27 +214,23 @@ class DMPLayer(nn.Module):
             self.dst_weight.div_(init_eeigenv)
             self.eloop_weight.div_(init_eeigenv)
 
-    def _use_fused(self):
-        if not self.fused:
-            return False
-        mlp_ok = self.num_mlp_layers == 0 or (self.num_mlp_layers == 2 and not self.batch_norm)
-        drop_ok = (not self.training) or self.drop.p == 0
-        return mlp_ok and drop_ok and supported_activation(self.act_func)
+    def _fused_mlps(self):
+        """(nmlp, emlp) as (MLPSpec, tensors) when the whole-layer function covers this configuration, else None."""
+        if not self.fused or not supported_activation(self.act_func):
+            return None
+        n, e = mlp_spec_and_tensors(self.nmlp), mlp_spec_and_tensors(self.emlp)
+        return None if n is None or e is None else (n, e)
 
     def forward(self, graph, node_feat, edge_feat):
         plan = get_plan(graph, REVFLAG, OUTDEGREE)
         # frame side effects of dmpnn.py:96-109 (inputs stay bound to the graph)
         graph.ndata[NODEFEAT] = node_feat
         graph.edata[EDGEFEAT] = edge_feat
-        if self._use_fused():
-            weights = (self.in_weight, self.out_weight, self.src_weight, self.dst_weight, self.nloop_weight,
-                       self.eloop_weight)
-            nmlp = emlp = None
-            if self.num_mlp_layers == 2:
-                nmlp = (self.nmlp[0].weight, self.nmlp[0].bias, self.nmlp[2].weight, self.nmlp[2].bias)
-                emlp = (self.emlp[0].weight, self.emlp[0].bias, self.emlp[2].weight, self.emlp[2].bias)
-            return fused_dmp_layer(plan, node_feat.float(), edge_feat.float(), weights, self.nbias, self.ebias,
-                                   nmlp, emlp, act_func=self.act_func, slope=LEAKY_RELU_A, order=_lib.ORDER_SCM)
+        mlps = self._fused_mlps()
+        if mlps is not None:
+            node_out, edge_out = _run_fused(self, plan, node_feat, edge_feat, mlps[0], mlps[1], act_func=self.act_func,
+                                            slope=LEAKY_RELU_A, order=_lib.ORDER_SCM)
+            return self.drop(node_out), self.drop(edge_out)       # dmpnn.py:138,154 (identity unless training with p > 0)
         node_pre, edge_pre = dual_message_passing(
             plan, node_feat, edge_feat, self.in_weight, self.out_weight, self.src_weight, self.dst_weight,
             self.nloop_weight, self.eloop_weight, self.nbias, self.ebias, order=_lib.ORDER_SCM)
@@ -230,6 +291,7 @@ class DualGraphConv(nn.Module):
         self.emlp = mlp()
         self.act = activation
         self.drop = nn.Dropout(dropout)
+        self.fused = "auto"   # False forces the composed autograd path (same kernels, torch-managed memory)
 
         for w in (self.in_weight, self.out_weight, self.src_weight, self.dst_weight, self.nloop_weight,
                   self.eloop_weight, self.nmlp[0].weight, self.nmlp[-1].weight, self.emlp[0].weight,
@@ -245,6 +307,22 @@ class DualGraphConv(nn.Module):
             self.dst_weight.div_(init_eeigenv)
             self.eloop_weight.div_(init_eeigenv)
 
+    def _fused_cfg(self):
+        """(nmlp, emlp, mlp activation, slope, post activation) when the whole-layer function covers this module."""
+        if not self.fused:
+            return None
+        n, e = mlp_spec_and_tensors(self.nmlp), mlp_spec_and_tensors(self.emlp)
+        if n is None or e is None or n[0].n_lin != 2:
+            return None
+        inner = _act_of_module(self.nmlp[-2])                 # model.py:148,154: LeakyReLU(1/5.5) or `activation`
+        post = _act_of_module(self.act)                        # model.py:247-248
+        if inner is None or post is None or self.emlp[-2].__class__ is not self.nmlp[-2].__class__:
+            return None
+        if inner[0] == "leaky_relu" and post[0] == "leaky_relu" and inner[1] != post[1]:
+            return None
+        slope = inner[1] if inner[0] == "leaky_relu" else post[1]
+        return n, e, inner[0], slope, post[0]
+
     def forward(self, graph, node_feat, edge_feat, edge_norm=None):
         plan = get_plan(graph, UNC_REVFLAG, UNC_OUTDEGREE)
         graph.ndata[UNC_FEAT] = node_feat
@@ -252,6 +330,16 @@ class DualGraphConv(nn.Module):
         if edge_norm is not None:
             graph.edata[UNC_NORM] = edge_norm
         norm = graph.edata[UNC_NORM] if UNC_NORM in graph.edata else None  # model.py:234: key presence decides
+        cfg = self._fused_cfg()
+        if cfg is not None:
+            # model.py:245,260: `self.drop(out)` is called and its result DISCARDED -- a numerical no-op that only
+            # advances the RNG in training mode; mirrored for RNG-stream parity
+            if self.training and self.drop.p > 0:
+                self.drop(torch.empty((plan.N, self.hidden_dim), device=node_feat.device))
+                self.drop(torch.empty((plan.E, self.hidden_dim), device=node_feat.device))
+            nmlp, emlp, act_name, slope, post = cfg
+            return _run_fused(self, plan, node_feat, edge_feat, nmlp, emlp, act_func=act_name, slope=slope,
+                              order=_lib.ORDER_UNC, norm=norm, post_act=post)
         node_pre, edge_pre = dual_message_passing(
             plan, node_feat, edge_feat, self.in_weight, self.out_weight, self.src_weight, self.dst_weight,
             self.nloop_weight, self.eloop_weight, self.nbias, self.ebias, norm=norm, order=_lib.ORDER_UNC)

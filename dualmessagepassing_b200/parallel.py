@@ -23,7 +23,7 @@ import torch.distributed as dist
 
 from . import _lib
 from .constants import LEAKY_RELU_A
-from .fused import _FusedDMPLayer, _ACT
+from .fused import _ACT, fused_dmp_layer, mlp_spec_and_tensors
 from .plan import DMPPlan
 
 
@@ -46,6 +46,41 @@ def reduce_scatter_rows(x, group=None):
     y = x.clone()
     dist.all_reduce(y, op=dist.ReduceOp.SUM, group=group)
     return y[rank * rows:(rank + 1) * rows].clone()
+
+
+class _Work:
+    """Handle of an asynchronous collective that keeps its buffers alive until it has been waited for."""
+
+    def __init__(self, work=None, keep=None):
+        self.work, self.keep = work, keep
+
+    def wait(self):
+        if self.work is not None:
+            self.work.wait()
+        self.work = self.keep = None
+        return True
+
+
+def all_gather_rows_async(x, group=None):
+    """(out, work): the all-gather is enqueued on the communicator's own stream; `work.wait()` makes the CURRENT stream
+    wait for it.  Whatever the caller launches in between overlaps the transfer (NVLink/NVSwitch: no SM contention)."""
+    world = dist.get_world_size(group)
+    out = torch.empty((x.shape[0] * world,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    x = x.contiguous()
+    work = dist.all_gather_into_tensor(out, x, group=group, async_op=True)
+    return out, _Work(work, x)
+
+
+def reduce_scatter_rows_async(x, group=None):
+    """(out, work) -- see all_gather_rows_async; `x` must stay alive (and unmodified) until work.wait()."""
+    world = dist.get_world_size(group)
+    rows = x.shape[0] // world
+    if dist.get_backend(group) == "nccl":
+        out = torch.empty((rows,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        x = x.contiguous()
+        work = dist.reduce_scatter_tensor(out, x, op=dist.ReduceOp.SUM, group=group, async_op=True)
+        return out, _Work(work, x)    # the input buffer must outlive the collective
+    return reduce_scatter_rows(x, group), _Work()
 
 
 def allreduce_gradients(params, group=None, average=True):
@@ -107,8 +142,9 @@ class PartitionedDMPLayer:
     parameter gradients it leaves in `.grad` are already summed over ranks."""
 
     def __init__(self, layer, src, dst, rev, num_nodes, rank, world, device, group=None):
-        if layer.num_mlp_layers not in (0, 2) or (layer.num_mlp_layers == 2 and layer.batch_norm):
-            raise NotImplementedError("partitioned execution needs a BatchNorm-free DMPLayer with 0 or 2 MLP layers")
+        if layer.num_mlp_layers > 1 and layer.batch_norm:
+            raise NotImplementedError("partitioned execution needs a BatchNorm-free DMPLayer (the batch statistics "
+                                      "would have to be all-reduced across ranks)")
         if layer.act_func not in _ACT:
             raise NotImplementedError("activation %r" % layer.act_func)
         self.layer, self.rank, self.world, self.group, self.device = layer, rank, world, group, device
@@ -131,11 +167,8 @@ class PartitionedDMPLayer:
 
     def __call__(self, node_feat_local, edge_feat_local):
         L = self.layer
-        has_mlp = L.num_mlp_layers == 2
-        cfg = (_lib.ORDER_SCM, _ACT[L.act_func], float(LEAKY_RELU_A), has_mlp)
-        n = (L.nmlp[0].weight, L.nmlp[0].bias, L.nmlp[2].weight, L.nmlp[2].bias) if has_mlp else (None,) * 4
-        e = (L.emlp[0].weight, L.emlp[0].bias, L.emlp[2].weight, L.emlp[2].bias) if has_mlp else (None,) * 4
-        part = (self.n_lo, self.n_hi, self.group)
-        return _FusedDMPLayer.apply(self.plan, cfg, node_feat_local.contiguous(), edge_feat_local.contiguous(),
-                                    None, L.in_weight, L.out_weight, L.src_weight, L.dst_weight,
-                                    L.nloop_weight, L.eloop_weight, L.nbias, L.ebias, *n, *e, part)
+        weights = (L.in_weight, L.out_weight, L.src_weight, L.dst_weight, L.nloop_weight, L.eloop_weight)
+        return fused_dmp_layer(self.plan, node_feat_local, edge_feat_local, weights, L.nbias, L.ebias,
+                               mlp_spec_and_tensors(L.nmlp), mlp_spec_and_tensors(L.emlp), act_func=L.act_func,
+                               slope=LEAKY_RELU_A, order=_lib.ORDER_SCM, training=L.training,
+                               part=(self.n_lo, self.n_hi, self.group))

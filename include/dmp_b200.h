@@ -135,6 +135,8 @@ DMP_API int dmp_segment_reduce(const int32_t* indptr, const int32_t* eid, const 
  * S = X_e*W_eloop, P = X_e*(W_src-W_dst), Qd = X_v*W_dst, Qs = X_v*W_src are produced by the dense
  * stage.  edge_agg (optional, may be NULL) receives msg, mirroring the reference's frame side effect
  * `edata["edge_agg"]` (dmpnn.py:126).  out may alias S.
+ * P may be NULL: S then already holds `eloop + add` (DMP_DUAL_STORE output of dmp_gemm_tf32x3_dual, rounded like the
+ * reference's `matmul(h, eloop) + add`), and out = (S + msg) + ebias -- the SCM association, bit for bit.
  */
 DMP_API int dmp_edge_update(const int32_t* a32, const int32_t* b32, const float* coef,
                     const float* S, int64_t ldS, const float* P, int64_t ldP,
@@ -191,6 +193,23 @@ DMP_API int dmp_gemm_tf32x3(const float* A, int64_t lda, const float* row_scale,
                             const float* bias, const float* aux, int64_t ld_aux, float* D, int64_t ldd,
                             int64_t M, int64_t N, int64_t K, int epilogue, float slope, void* stream);
 
+/* Two projections of the SAME streamed operand in one pass (the operand is read from HBM once, both products stay in
+ * tensor memory):
+ *   DMP_DUAL_STORE        D[r,:]  = A[r,:]·W1t^T + row_scale[r] * (A[r,:]·W2t^T)
+ *   DMP_DUAL_ACCUMULATE   D[r,:]  = (D[r,:] + A[r,:]·W1t^T) + row_scale[r] * (A[r,:]·W2t^T)
+ *   DMP_DUAL_SEPARATE     D = A·W1t^T ,  D2 = A·W2t^T                (row_scale must be NULL)
+ * W1t, W2t are [N,K] (nn.Linear layout) with a common leading dimension; N, K in {64,128}.  Replaces the pair
+ * `matmul(h, eloop_weight) + 2*(1+d) * matmul(h, src_weight - dst_weight)` of dmpnn.py:146-147 (STORE: the sum is
+ * rounded exactly like `eloop + add`, so dmp_edge_update takes it as S with P = NULL; SEPARATE for the UNC association
+ * order of model.py:257) and its autograd transpose `dX_e += gE·W_eloop^T + (coef ⊙ gE)·(W_src-W_dst)^T` (ACCUMULATE).
+ * row_scale may be NULL (= 1). */
+#define DMP_DUAL_STORE 0
+#define DMP_DUAL_ACCUMULATE 1
+#define DMP_DUAL_SEPARATE 2
+DMP_API int dmp_gemm_tf32x3_dual(const float* A, int64_t lda, const float* W1t, const float* W2t, int64_t ldw,
+                                 const float* row_scale, float* D, int64_t ldd, float* D2, int64_t ldd2,
+                                 int64_t M, int64_t N, int64_t K, int mode, void* stream);
+
 /* Backward of `fn.sum` folded into the edge-gradient projection (no [E,H] message-gradient tensor is materialised):
  *   D[r,:] += (row_scale ⊙ A)[r,:] · Bt^T + sgn_r * norm_r * tab_{rev_r}[dst32[r], :]      sgn_r = rev[r] ? +1 : -1
  * with tab_fwd = gN·W_in^T, tab_rev = gN·W_out^T (node-sized).  rev / norm / row_scale may be NULL. */
@@ -214,6 +233,29 @@ DMP_API int dmp_gemm_tn_workspace_bytes(int64_t M, int64_t N, int64_t* bytes_hos
 DMP_API int dmp_gemm_tn_tf32x3(const float* X, int64_t ldx, const float* row_scale, const float* G, int64_t ldg,
                                float* D, int64_t ldd, float* colsum_x, float* colsum_g, int64_t E, int64_t M,
                                int64_t N, int accumulate, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * BatchNorm1d between the two Linears of the node / edge MLP (dmpnn.py:45-52 with batch_norm=True -- the class
+ * default; UNC model.py:145-156 always).  The statistics run over all node rows / all edge rows, so this cannot be a
+ * GEMM epilogue; it is column-reduction + elementwise work, deterministic (fixed-order partial sums, no float atomics).
+ *   dmp_bn_stats      mean[c] = sum_r x[r,c] / rows ;  var[c] = sum_r (x[r,c] - mean[c])^2 / rows      (two passes)
+ *   dmp_bn_act        out = act(((x - mean) * invstd) * gamma + beta)              gamma / beta may be NULL
+ *   dmp_bn_backward   dbeta = sum_r g, dgamma = sum_r g * xhat, and
+ *                     gx = gamma*invstd * (g - dbeta/rows - xhat*dgamma/rows)   (training != 0: batch statistics)
+ *                     gx = gamma*invstd * g                                     (training == 0: running statistics)
+ *                     gx may alias g.
+ * workspace: dmp_bn_workspace_bytes(H) bytes, ZERO-INITIALISED ONCE by the caller (the kernels leave it zeroed).
+ */
+DMP_API int dmp_bn_workspace_bytes(int64_t H, int64_t* bytes_host);
+DMP_API int dmp_bn_stats(const float* x, int64_t ldx, int64_t rows, int64_t H, float* mean, float* var,
+                         void* workspace, int64_t workspace_bytes, void* stream);
+DMP_API int dmp_bn_act(const float* x, int64_t ldx, const float* mean, const float* invstd, const float* gamma,
+                       const float* beta, float* out, int64_t ld_out, int64_t rows, int64_t H, int act, float slope,
+                       void* stream);
+DMP_API int dmp_bn_backward(const float* g, int64_t ldg, const float* x, int64_t ldx, const float* mean,
+                            const float* invstd, const float* gamma, float* gx, int64_t ld_gx, float* dgamma,
+                            float* dbeta, int64_t rows, int64_t H, int training, void* workspace,
+                            int64_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }
