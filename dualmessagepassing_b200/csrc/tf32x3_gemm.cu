@@ -26,6 +26,12 @@
 namespace dmp {
 namespace gemm {
 
+// tf32x3_gemm_v2.cu: 64-row tiles, cross-terms-first MMA order (lower truncation error); every product whose row scale
+// (if any) rides on the accumulator goes there; this file keeps producer-side row scales and the gather epilogue
+int launch_gemm_v2(const float* A, int64_t lda, const float* Wt, int64_t ldw, const float* scale, const float* bias,
+                   const float* aux, int64_t ld_aux, float* D, int64_t ldd, int64_t M, int64_t N, int64_t K, int mode,
+                   int act, float slope, cudaStream_t stream);
+
 constexpr int kProducerWarps = 8;
 constexpr int kProducerThreads = kProducerWarps * 32;
 constexpr int kEpilogueWarps = 8;        // two warps per TMEM lane quadrant, each takes half of the columns
@@ -797,8 +803,12 @@ extern "C" int dmp_gemm_tf32x3(const float* A, int64_t lda, const float* row_sca
   else if (bias != nullptr || act != DMP_ACT_NONE) mode = kModeBiasPwl;
   else mode = kModeStore;
   p.epi_scale = nullptr;
-  if (mode == kModeAccumulate && N == 128 && row_scale != nullptr) { p.epi_scale = row_scale; p.row_scale = nullptr; }
+  if (mode == kModeAccumulate && row_scale != nullptr) { p.epi_scale = row_scale; p.row_scale = nullptr; }
   cudaStream_t s = (cudaStream_t)stream;
+  static const bool use_v2 = [] { const char* e = getenv("DMP_GEMM_V2"); return e ? atoi(e) != 0 : true; }();
+  if (use_v2 && p.row_scale == nullptr)   // epilogue-mode ids coincide (kModeStore..kModeGradSmooth = 0..5)
+    return launch_gemm_v2(A, lda, Bt, ldb, p.epi_scale, bias, aux, ld_aux, D, ldd, M, N, K, mode, act, p.slope, s);
+  if (p.epi_scale != nullptr && N == 64) { p.row_scale = p.epi_scale; p.epi_scale = nullptr; }   // legacy N = 64: scale on A
   if (N == 128 && K == 128) return launch_gemm<128, 128>(p, mode, s);
   if (N == 128 && K == 64) return launch_gemm<128, 64>(p, mode, s);
   if (N == 64 && K == 128) return launch_gemm<64, 128>(p, mode, s);

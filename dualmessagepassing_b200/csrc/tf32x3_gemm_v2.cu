@@ -1,0 +1,519 @@
+// tf32x3_gemm_v2.cu -- row-streaming projections on the tcgen05 tensor cores, 3xTF32 split, CROSS-TERMS-FIRST.
+//
+//   single   D[M,128]  = epilogue( (A[M,K]) · Wt[128,K]^T )                         (dmp_gemm_tf32x3, N = 128)
+//   dual     D[M,N] (+)= A·W1t^T + c ⊙ (A·W2t^T)   |   D1 = A·W1t^T, D2 = A·W2t^T    (dmp_gemm_tf32x3_dual, N in {64,128})
+//
+// Accuracy.  The tensor core accumulates in fp32 with TRUNCATION (round toward zero), not round-to-nearest.  Round 1
+// issued the three products of the split (lo·hi, hi·lo, hi·hi) interleaved per k-step, so every one of the 48 MMAs of
+// a K = 128 row tile truncated an accumulator that already held the large hi·hi partial sums: a systematic 1.2e-6
+// (max-norm, vs fp64) against 4.6e-7 for an fp32 FMA GEMM.  Here a tile is 64 rows with ALL of K resident in shared
+// memory, and the MMAs are issued cross terms first (32 MMAs into a still-small accumulator: their truncation is 2^-11
+// smaller), the 16 hi·hi MMAs last: a bit-level model of the accumulator predicts 6.6e-7 (tests/test_gpu_gemm.py
+// asserts <= 1.0e-6; measured value in DESIGN.md).
+//
+// Structure (one persistent CTA per SM, 17 warps):
+//   warps 9..16  PRODUCERS  one elected thread issues K/32 TMA boxes (64 rows x 32 floats, SWIZZLE_128B) per tile onto
+//                           the stage's mbarrier (expect_tx); the raw tile IS the hi operand (kind::tf32 ignores the low
+//                           13 mantissa bits); the warps then write lo = x - trunc_tf32(x).  Without TMA (M < 64 or
+//                           encoder unavailable): per-thread cp.async.
+//   warp  8      MMA        weights live in TENSOR MEMORY as the A operand ("TS" form, transposed product
+//                           D^T[feature, row] = W[feature, k] · X[row, k]^T: a TMEM lane is an output feature, the 32
+//                           lanes of an epilogue warp store 32 consecutive floats of one output row)
+//   warps 0..7   EPILOGUE   4 accumulator buffers of 64 columns in TMEM; warp (quadrant q, half h) owns features
+//                           32q.. and rows 32h.. of the tile.
+// Dual form: lanes 0..63 = rows f0.. of W1, lanes 64..127 = the same rows of W2; acc1[f, r] sits in quadrant q, acc2[f, r]
+// in quadrant q+2 -- different warps by the hardware's lane-quadrant rule -- so the two warps swap half of their rows
+// through shared memory (named barrier per pair) and each finalises 16 rows.  For N = 128 two CTAs (blockIdx parity =
+// feature half) walk the same tiles in the same order: the second read of a tile hits L2.
+#include "tc_common.cuh"
+
+namespace dmp {
+namespace gemm {
+
+constexpr int kV2Rows = 64;                         // rows per tile = MMA N
+constexpr int kV2ProducerWarps = 8;
+constexpr int kV2EpilogueWarps = 8;
+constexpr int kV2MmaWarp = 8;
+constexpr int kV2Threads = (kV2EpilogueWarps + 1 + kV2ProducerWarps) * 32;   // 544
+constexpr int kV2AccBufs = 4;                       // TMEM accumulator ring: 4 x 64 columns
+constexpr int kV2XchgBytes = 8 * 2048;              // dual: per epilogue warp 16 rows x 32 features
+
+enum : int {
+  kV2Store = 0, kV2Accumulate = 1, kV2BiasPwl = 2, kV2GradPwl = 3, kV2BiasSmooth = 4, kV2GradSmooth = 5,   // single
+  kV2AccumulateScaled = 6,                         // D += s_r * acc_r (row scale applied to the accumulator)
+  kV2DualStore = 8, kV2DualAccumulate = 9, kV2DualSeparate = 10,                                            // dual
+};
+
+template <int K>
+struct V2Smem {
+  static constexpr int kKBlocks = K / kKB;
+  static constexpr int kBlockBytes = kV2Rows * 128;             // one k-block (64 rows x 32 floats): 8 KB
+  static constexpr int kHalfBytes = kKBlocks * kBlockBytes;     // hi or lo of one tile
+  static constexpr int kStageBytes = 2 * kHalfBytes;            // 64 KB (K = 128) / 32 KB (K = 64)
+  static constexpr int kStages = (K == 128) ? 3 : 6;
+  static constexpr int kTotal = kStages * kStageBytes + kV2XchgBytes + 256 + 1024;
+};
+
+struct V2Params {
+  const float* A; int64_t lda;
+  const float* W1; const float* W2; int64_t ldw;   // [N, K] (nn.Linear layout); W2 only in the dual forms
+  const float* scale;                              // single/accumulate: D += s_r * acc_r; dual: c_r
+  const float* bias;
+  const float* aux; int64_t ld_aux;
+  float* D; int64_t ldd;
+  float* D2; int64_t ldd2;
+  int64_t M;
+  int act; float slope;
+  int use_tma;
+};
+
+template <int MODE>
+__device__ __forceinline__ float v2_epilogue_op(float acc, float bias, float aux, float old, float slope, int act) {
+  if constexpr (MODE == kV2Store) return acc;
+  if constexpr (MODE == kV2Accumulate || MODE == kV2AccumulateScaled) return __fadd_rn(old, acc);
+  if constexpr (MODE == kV2BiasPwl) {
+    const float x = __fadd_rn(acc, bias);
+    return x > 0.0f ? x : __fmul_rn(x, slope);
+  }
+  if constexpr (MODE == kV2GradPwl) return __fmul_rn(acc, aux > 0.0f ? 1.0f : slope);
+  if constexpr (MODE == kV2BiasSmooth) return apply_act(__fadd_rn(acc, bias), act, slope);
+  return __fmul_rn(acc, act_grad_from_output(aux, act, slope));
+}
+
+// NOUT: output features (dual: 64 or 128; single: 128).  DUAL: two weights stacked on the TMEM lanes.
+template <int NOUT, int K, int MODE>
+__global__ void __launch_bounds__(kV2Threads, 1) tf32x3_gemm_v2_kernel(const V2Params p,
+                                                                       const __grid_constant__ CUtensorMap tmap) {
+  using L = V2Smem<K>;
+  constexpr bool kDual = MODE >= kV2DualStore;
+  constexpr int kKBlocks = L::kKBlocks;
+  constexpr int kStages = L::kStages;
+  constexpr int kHalves = kDual ? NOUT / 64 : 1;              // CTAs per row tile (dual, N = 128: feature halves)
+  // single-weight form with NOUT = 64: lanes 64..127 carry zero weights (the MMA is still M = 128; at 64 features the
+  // doubled tensor work stays hidden behind the HBM stream) and their epilogue warps only release the accumulator
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = base;                                   // stage s: [hi: kKBlocks x 8 KB][lo: kKBlocks x 8 KB]
+  const uint32_t sX = sA + kStages * L::kStageBytes;          // dual exchange buffer: warp w writes [w*2048, +2048)
+  const uint32_t sBar = sX + kV2XchgBytes;
+  const uint32_t bar_full = sBar;                             // kStages x 8 B   (lo written, hi landed)
+  const uint32_t bar_empty = sBar + 8 * kStages;              // MMAs of the stage retired
+  const uint32_t bar_raw = sBar + 16 * kStages;               // TMA completion of the raw (= hi) tile
+  const uint32_t bar_acc_full = sBar + 24 * kStages;          // kV2AccBufs x 8 B
+  const uint32_t bar_acc_empty = bar_acc_full + 8 * kV2AccBufs;
+  const uint32_t tmem_slot = bar_acc_empty + 8 * kV2AccBufs;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int fh = (kHalves == 2) ? (int)(blockIdx.x & 1) : 0;
+  const int64_t tile0 = (kHalves == 2) ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x;
+  const int64_t tstep = (kHalves == 2) ? (int64_t)(gridDim.x >> 1) : (int64_t)gridDim.x;
+  const int64_t num_tiles = (p.M + kV2Rows - 1) / kV2Rows;
+  const int64_t my_tiles = tile0 < num_tiles ? (num_tiles - tile0 + tstep - 1) / tstep : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(bar_full + 8 * s, kV2ProducerWarps);
+      mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_raw + 8 * s, 1);
+    }
+    for (int a = 0; a < kV2AccBufs; ++a) {
+      mbar_init(bar_acc_full + 8 * a, 1);
+      mbar_init(bar_acc_empty + 8 * a, kV2EpilogueWarps);
+    }
+    fence_barrier_init();
+  }
+  // TMEM map: [0,256) 4 accumulators of 64 columns | [256,256+K) W hi | [256+K,256+2K) W lo
+  constexpr int kTmemCols = 512;
+  constexpr uint32_t kWhiCol = 256, kWloCol = 256 + K;
+  if (warp == kV2MmaWarp) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  if (warp < 4) {   // thread = TMEM lane = weight row (single) | (weight, row) (dual); hi = tf32(w), lo = w - hi
+    const int l = warp * 32 + lane;
+    const float* wrow;
+    if constexpr (kDual) wrow = ((l < 64) ? p.W1 : p.W2) + (int64_t)(fh * 64 + (l & 63)) * p.ldw;
+    else wrow = p.W1 + (int64_t)(l < NOUT ? l : 0) * p.ldw;
+    const bool zero_row = !kDual && l >= NOUT;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+    for (int c0 = 0; c0 < K; c0 += 32) {
+      float hi[32], lo[32];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float4 v = __ldg(reinterpret_cast<const float4*>(wrow + c0 + 4 * q));
+        if (zero_row) v = make_float4(0.f, 0.f, 0.f, 0.f);
+        hi[4 * q + 0] = tf32_rna(v.x); lo[4 * q + 0] = __fsub_rn(v.x, hi[4 * q + 0]);
+        hi[4 * q + 1] = tf32_rna(v.y); lo[4 * q + 1] = __fsub_rn(v.y, hi[4 * q + 1]);
+        hi[4 * q + 2] = tf32_rna(v.z); lo[4 * q + 2] = __fsub_rn(v.z, hi[4 * q + 2]);
+        hi[4 * q + 3] = tf32_rna(v.w); lo[4 * q + 3] = __fsub_rn(v.w, hi[4 * q + 3]);
+      }
+      tmem_st32(t_lane + kWhiCol + c0, hi);
+      tmem_st32(t_lane + kWloCol + c0, lo);
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (warp > kV2MmaWarp) {
+    // =========================== PRODUCERS ===========================
+    const int pt = threadIdx.x - (kV2MmaWarp + 1) * 32;        // 0..255
+    // thread handles 16-byte chunks c = pt + 256 i of a k-block: row = c / 8 (0..63 over i < 2), chunk = c % 8
+    const int c16 = pt & 7;
+    const int row0 = pt >> 3;                                   // rows row0, row0 + 32
+    uint32_t offs[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) offs[i] = swz(row0 + 32 * i, c16);
+    constexpr int kAhead = kStages - 1;                         // tiles of copies in flight
+    int istage = 0;
+    uint32_t iphase = 0;
+    int64_t itile = 0;
+    auto issue = [&]() {                                        // start the copies of local tile `itile`
+      mbar_wait(bar_empty + 8 * istage, iphase ^ 1);
+      const uint32_t hi = sA + istage * L::kStageBytes;
+      const int64_t r0 = (tile0 + itile * tstep) * kV2Rows;
+      if (p.use_tma) {
+        if (pt == 0) {
+          mbar_expect_tx(bar_raw + 8 * istage, L::kHalfBytes);
+#pragma unroll
+          for (int kb = 0; kb < kKBlocks; ++kb)
+            tma_load_2d(hi + kb * L::kBlockBytes, &tmap, kb * kKB, (int)r0, bar_raw + 8 * istage);
+        }
+      } else {
+        const float* src = p.A + (r0 + row0) * p.lda + c16 * 4;
+#pragma unroll
+        for (int kb = 0; kb < kKBlocks; ++kb) {
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const bool ok = r0 + row0 + 32 * i < p.M;
+            cp_async16(hi + kb * L::kBlockBytes + offs[i],
+                       ok ? (const void*)(src + (int64_t)(32 * i) * p.lda + kb * kKB) : (const void*)p.A, ok ? 16u : 0u);
+          }
+        }
+      }
+      ++itile;
+      if (++istage == kStages) { istage = 0; iphase ^= 1; }
+    };
+#pragma unroll 1
+    for (int d = 0; d < kAhead; ++d) {
+      if (d < my_tiles) issue();
+      cp_async_commit();
+    }
+    int stage = 0;
+    uint32_t rphase = 0;
+#pragma unroll 1
+    for (int64_t t = 0; t < my_tiles; ++t) {
+      if (p.use_tma) mbar_wait(bar_raw + 8 * stage, rphase);
+      else cp_async_wait<kAhead - 1>();
+      const uint32_t hi = sA + stage * L::kStageBytes;
+      const uint32_t lo = hi + L::kHalfBytes;
+#pragma unroll
+      for (int kb = 0; kb < kKBlocks; ++kb) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const float4 v = lds128(hi + kb * L::kBlockBytes + offs[i]);
+          sts128(lo + kb * L::kBlockBytes + offs[i],
+                 make_float4(tf32_trunc_residual(v.x), tf32_trunc_residual(v.y), tf32_trunc_residual(v.z),
+                             tf32_trunc_residual(v.w)));
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_full + 8 * stage);
+      if (++stage == kStages) { stage = 0; rphase ^= 1; }
+      if (t + kAhead < my_tiles) issue();
+      cp_async_commit();
+    }
+  } else if (warp == kV2MmaWarp) {
+    // =========================== MMA ISSUER ===========================
+    constexpr uint32_t idesc = make_idesc(128, kV2Rows);
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+#pragma unroll 1
+    for (int64_t t = 0; t < my_tiles; ++t) {
+      mbar_wait(bar_acc_empty + 8 * acc, acc_phase ^ 1);
+      mbar_wait(bar_full + 8 * stage, phase);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kV2Rows);
+        const uint32_t a_hi = sA + stage * L::kStageBytes;
+        const uint32_t a_lo = a_hi + L::kHalfBytes;
+        // cross terms first (the accumulator is still small: their truncation is harmless), dominant hi*hi last
+#pragma unroll
+        for (int kb = 0; kb < kKBlocks; ++kb) {
+#pragma unroll
+          for (int j = 0; j < kKB / 8; ++j) {
+            const uint64_t dah = make_smem_desc(a_hi + kb * L::kBlockBytes + j * 32);
+            const uint64_t dal = make_smem_desc(a_lo + kb * L::kBlockBytes + j * 32);
+            const uint32_t w_hi = tmem_base + kWhiCol + (uint32_t)(kb * kKB + j * 8);
+            const uint32_t w_lo = tmem_base + kWloCol + (uint32_t)(kb * kKB + j * 8);
+            umma_tf32_ts(d_tmem, w_hi, dal, idesc, (kb | j) != 0 ? 1u : 0u);
+            umma_tf32_ts(d_tmem, w_lo, dah, idesc, 1u);
+          }
+        }
+#pragma unroll
+        for (int kb = 0; kb < kKBlocks; ++kb) {
+#pragma unroll
+          for (int j = 0; j < kKB / 8; ++j) {
+            const uint64_t dah = make_smem_desc(a_hi + kb * L::kBlockBytes + j * 32);
+            const uint32_t w_hi = tmem_base + kWhiCol + (uint32_t)(kb * kKB + j * 8);
+            umma_tf32_ts(d_tmem, w_hi, dah, idesc, 1u);
+          }
+        }
+        umma_commit(bar_empty + 8 * stage);                   // smem stage free once these MMAs retire
+        umma_commit(bar_acc_full + 8 * acc);
+      }
+      __syncwarp();
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
+      if (++acc == kV2AccBufs) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // =========================== EPILOGUE ===========================
+    const int quad = warp & 3, half = warp >> 2;     // TMEM lane quadrant (hardware rule: warp % 4), row half (32 rows)
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    if constexpr (!kDual) {
+      constexpr bool kNeedAux = (MODE == kV2GradPwl || MODE == kV2GradSmooth);
+      constexpr bool kNeedBias = (MODE == kV2BiasPwl || MODE == kV2BiasSmooth);
+      constexpr bool kNeedOld = (MODE == kV2Accumulate || MODE == kV2AccumulateScaled);
+      constexpr bool kScaled = (MODE == kV2AccumulateScaled);
+      const int f = quad * 32 + lane;
+      const bool live = quad * 32 < NOUT;               // NOUT = 64: quadrants 2, 3 hold the zero rows
+      const float bias_f = (kNeedBias && live && p.bias != nullptr) ? __ldg(p.bias + f) : 0.0f;
+#pragma unroll 1
+      for (int64_t t = 0; t < my_tiles; ++t) {
+        if (!live) {                                    // warp-uniform
+          mbar_wait(bar_acc_full + 8 * acc, acc_phase);
+          if (lane == 0) mbar_arrive(bar_acc_empty + 8 * acc);
+          if (++acc == kV2AccBufs) { acc = 0; acc_phase ^= 1; }
+          continue;
+        }
+        const int64_t r0 = (tile0 + t * tstep) * kV2Rows + half * 32;
+        const int nvalid = (int)((p.M - r0) < 32 ? (p.M - r0) : 32);     // warp-uniform, may be <= 0
+        float* dst = p.D + r0 * p.ldd + f;
+        float tt[32];
+        if constexpr (kNeedAux || kNeedOld) {
+          // streamed epilogue operand requested BEFORE waiting for this tile's MMAs: its DRAM latency hides behind them
+          const float* src = kNeedAux ? p.aux + r0 * p.ld_aux + f : dst;
+          const int64_t lds = kNeedAux ? p.ld_aux : p.ldd;
+          if (nvalid == 32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) tt[j] = src[j * lds];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) tt[j] = j < nvalid ? src[j * lds] : 0.0f;
+          }
+        }
+        float sc_l = 1.0f;
+        if (kScaled && lane < nvalid) sc_l = __ldg(p.scale + r0 + lane);
+        mbar_wait(bar_acc_full + 8 * acc, acc_phase);
+        tc_fence_after();
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kV2Rows + half * 32), v);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_acc_empty + 8 * acc);
+        // accumulate reads and writes the same addresses: hide that from the compiler, or it keeps all 32 load addresses
+        // (64 registers) alive across the accumulator wait for re-use by the stores and spills
+        asm volatile("" : "+l"(dst));
+        if constexpr (kScaled) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __fmul_rn(__shfl_sync(0xffffffffu, sc_l, j), v[j]);
+        }
+        if (nvalid == 32) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            dst[j * p.ldd] = v2_epilogue_op<MODE>(v[j], bias_f, kNeedAux ? tt[j] : 0.0f, kNeedOld ? tt[j] : 0.0f, p.slope, p.act);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nvalid)
+              dst[j * p.ldd] = v2_epilogue_op<MODE>(v[j], bias_f, kNeedAux ? tt[j] : 0.0f, kNeedOld ? tt[j] : 0.0f, p.slope, p.act);
+        }
+        if (++acc == kV2AccBufs) { acc = 0; acc_phase ^= 1; }
+      }
+    } else {
+      const int which = quad >> 1;                     // 0: this warp holds acc1 (W1), 1: acc2 (W2)
+      const int f = fh * 64 + (quad & 1) * 32 + lane;  // output feature of this thread
+      const uint32_t my_x = sX + (uint32_t)warp * 2048u + (uint32_t)lane * 4u;           // [row j][lane] floats
+      const uint32_t peer_x = sX + (uint32_t)(warp ^ 2) * 2048u + (uint32_t)lane * 4u;   // written by quadrant q^2, same half
+      const int bar_id = 1 + (quad & 1) * 2 + half;    // named barrier of the pair (ids 1..4), 64 threads
+#pragma unroll 1
+      for (int64_t t = 0; t < my_tiles; ++t) {
+        const int64_t rt = (tile0 + t * tstep) * kV2Rows + half * 32;     // first of this warp's 32 rows
+        const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kV2Rows + half * 32);
+        if constexpr (MODE == kV2DualSeparate) {
+          mbar_wait(bar_acc_full + 8 * acc, acc_phase);
+          tc_fence_after();
+          float v[32];
+          tmem_ld32(t_lane, v);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_acc_empty + 8 * acc);
+          float* out = which ? p.D2 : p.D;
+          const int64_t ldo = which ? p.ldd2 : p.ldd;
+          float* dst = out + rt * ldo + f;
+          const int nvalid = (int)((p.M - rt) < 32 ? (p.M - rt) : 32);
+          if (nvalid == 32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dst[j * ldo] = v[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nvalid) dst[j * ldo] = v[j];
+          }
+        } else {
+          // rows this warp finalises: 16 rows starting at r0 (acc1 warp: the first 16 of the pair's 32, acc2 warp: the rest)
+          const int64_t r0 = rt + which * 16;
+          const int nvalid = (int)((p.M - r0) < 16 ? (p.M - r0) : 16);     // warp-uniform, may be <= 0
+          float* dst = p.D + r0 * p.ldd + f;
+          float old[16];
+          if constexpr (MODE == kV2DualAccumulate) {
+            // previous D requested BEFORE waiting for this tile's MMAs
+#pragma unroll
+            for (int j = 0; j < 16; ++j) old[j] = j < nvalid ? dst[j * p.ldd] : 0.0f;
+          }
+          float sc_l = 1.0f;       // lane j (< 16) holds the scale of row r0 + j; broadcast by shuffle below
+          if (p.scale != nullptr && lane < nvalid) sc_l = __ldg(p.scale + r0 + lane);
+          mbar_wait(bar_acc_full + 8 * acc, acc_phase);
+          tc_fence_after();
+          float keep[16], send[16];
+          tmem_ld16(t_lane + (which ? 16 : 0), keep);           // the rows this warp finalises
+          tmem_ld16(t_lane + (which ? 0 : 16), send);           // the rows the partner finalises
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_acc_empty + 8 * acc);  // everything needed is out of TMEM
+          asm volatile("" : "+l"(dst));                         // see the single-weight accumulate epilogue
+          // the partner has finished reading what I wrote for the previous tile
+          asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(my_x + j * 128), "f"(send[j]) : "memory");
+          asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float got = lds32(peer_x + j * 128);
+            const float a1 = which ? got : keep[j];
+            const float a2 = which ? keep[j] : got;
+            const float c = __shfl_sync(0xffffffffu, sc_l, j);
+            float r = (MODE == kV2DualAccumulate) ? __fadd_rn(old[j], a1) : a1;
+            r = __fadd_rn(r, __fmul_rn(c, a2));
+            if (j < nvalid) dst[j * p.ldd] = r;
+          }
+        }
+        if (++acc == kV2AccBufs) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kV2MmaWarp) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// TMA descriptor of the streamed operand: fp32 [M rows x K], box = 64 rows x 32 floats, 128-byte swizzle
+static bool make_tmap_rows64(CUtensorMap* tmap, const float* A, int64_t lda, int64_t M, int K) {
+  TmapEncodeFn enc = tmap_encoder();
+  if (enc == nullptr || M > 0x7fffffffLL) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)M};
+  const cuuint64_t strides[1] = {(cuuint64_t)lda * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)kKB, (cuuint32_t)kV2Rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(A), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int NOUT, int K, int MODE>
+static int launch_v2_mode(const V2Params& p, cudaStream_t stream) {
+  using L = V2Smem<K>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tf32x3_gemm_v2_kernel<NOUT, K, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         L::kTotal);
+    if (e != cudaSuccess) {
+      set_error("gemm_tf32x3 (v2): cannot reserve %d bytes of shared memory: %s", L::kTotal, cudaGetErrorString(e));
+      return DMP_ERR_CUDA;
+    }
+    configured = true;
+  }
+  constexpr int kHalves = (MODE >= kV2DualStore) ? NOUT / 64 : 1;
+  const int64_t tiles = (p.M + kV2Rows - 1) / kV2Rows;
+  const int64_t streams = kNumSMs / kHalves;
+  const unsigned grid = (unsigned)((tiles < streams ? tiles : streams) * kHalves);
+  V2Params q = p;
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  q.use_tma = (tma_enabled() && p.M >= kV2Rows && make_tmap_rows64(&tmap, p.A, p.lda, p.M, K)) ? 1 : 0;
+  tf32x3_gemm_v2_kernel<NOUT, K, MODE><<<grid, kV2Threads, L::kTotal, stream>>>(q, tmap);
+  return launch_status("tf32x3_gemm_v2_kernel");
+}
+
+template <int NOUT, int K>
+static int launch_v2_single(const V2Params& p, int mode, cudaStream_t s) {
+  switch (mode) {
+    case kV2Store: return launch_v2_mode<NOUT, K, kV2Store>(p, s);
+    case kV2Accumulate: return launch_v2_mode<NOUT, K, kV2Accumulate>(p, s);
+    case kV2BiasPwl: return launch_v2_mode<NOUT, K, kV2BiasPwl>(p, s);
+    case kV2GradPwl: return launch_v2_mode<NOUT, K, kV2GradPwl>(p, s);
+    case kV2BiasSmooth: return launch_v2_mode<NOUT, K, kV2BiasSmooth>(p, s);
+    case kV2AccumulateScaled: return launch_v2_mode<NOUT, K, kV2AccumulateScaled>(p, s);
+    default: return launch_v2_mode<NOUT, K, kV2GradSmooth>(p, s);
+  }
+}
+
+template <int NOUT, int K>
+static int launch_v2_dual(const V2Params& p, int mode, cudaStream_t s) {
+  if (mode == DMP_DUAL_STORE) return launch_v2_mode<NOUT, K, kV2DualStore>(p, s);
+  if (mode == DMP_DUAL_ACCUMULATE) return launch_v2_mode<NOUT, K, kV2DualAccumulate>(p, s);
+  return launch_v2_mode<NOUT, K, kV2DualSeparate>(p, s);
+}
+
+// single-weight entry used by dmp_gemm_tf32x3 (tf32x3_gemm.cu); mode = kV2Store..kV2GradSmooth
+int launch_gemm_v2(const float* A, int64_t lda, const float* Wt, int64_t ldw, const float* scale, const float* bias,
+                   const float* aux, int64_t ld_aux, float* D, int64_t ldd, int64_t M, int64_t N, int64_t K, int mode,
+                   int act, float slope, cudaStream_t stream) {
+  V2Params p;
+  p.A = A; p.lda = lda; p.W1 = Wt; p.W2 = nullptr; p.ldw = ldw; p.scale = scale; p.bias = bias; p.aux = aux;
+  p.ld_aux = ld_aux; p.D = D; p.ldd = ldd; p.D2 = nullptr; p.ldd2 = 0; p.M = M; p.act = act; p.slope = slope; p.use_tma = 0;
+  if (mode == kV2Accumulate && scale != nullptr) mode = kV2AccumulateScaled;
+  if (N == 128) return K == 128 ? launch_v2_single<128, 128>(p, mode, stream) : launch_v2_single<128, 64>(p, mode, stream);
+  return K == 128 ? launch_v2_single<64, 128>(p, mode, stream) : launch_v2_single<64, 64>(p, mode, stream);
+}
+
+}  // namespace gemm
+}  // namespace dmp
+
+extern "C" int dmp_gemm_tf32x3_dual(const float* A, int64_t lda, const float* W1t, const float* W2t, int64_t ldw,
+                                    const float* row_scale, float* D, int64_t ldd, float* D2, int64_t ldd2,
+                                    int64_t M, int64_t N, int64_t K, int mode, void* stream) {
+  using namespace dmp;
+  using namespace dmp::gemm;
+  DMP_CHECK_ARG(M >= 0, "gemm_tf32x3_dual: negative M");
+  if (M == 0) return DMP_OK;
+  DMP_CHECK_ARG(A && W1t && W2t && D, "gemm_tf32x3_dual: null pointer");
+  DMP_CHECK_ARG(mode == DMP_DUAL_STORE || mode == DMP_DUAL_ACCUMULATE || mode == DMP_DUAL_SEPARATE,
+                "gemm_tf32x3_dual: bad mode %d", mode);
+  DMP_CHECK_ARG((N == 64 || N == 128) && (K == 64 || K == 128), "gemm_tf32x3_dual: N and K must be 64 or 128 (got %lld, %lld)",
+                (long long)N, (long long)K);
+  DMP_CHECK_ARG(lda >= K && ldw >= K && ldd >= N && lda % 4 == 0 && ldw % 4 == 0,
+                "gemm_tf32x3_dual: leading dimensions must be >= the row length (A, W: multiples of 4)");
+  DMP_CHECK_ARG(aligned_to(A, 16) && aligned_to(W1t, 16) && aligned_to(W2t, 16),
+                "gemm_tf32x3_dual: A and the weights must be 16-byte aligned");
+  DMP_CHECK_ARG(mode != DMP_DUAL_SEPARATE || (D2 != nullptr && ldd2 >= N && row_scale == nullptr),
+                "gemm_tf32x3_dual: separate mode needs D2 and takes no row scale");
+  DMP_CHECK_ARG(A != D && A != D2, "gemm_tf32x3_dual: outputs must not alias A");
+  V2Params p;
+  p.A = A; p.lda = lda; p.W1 = W1t; p.W2 = W2t; p.ldw = ldw; p.scale = row_scale; p.bias = nullptr; p.aux = nullptr;
+  p.ld_aux = 0; p.D = D; p.ldd = ldd; p.D2 = D2; p.ldd2 = ldd2; p.M = M; p.act = 0; p.slope = 1.0f; p.use_tma = 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (N == 128 && K == 128) return launch_v2_dual<128, 128>(p, mode, s);
+  if (N == 128 && K == 64) return launch_v2_dual<128, 64>(p, mode, s);
+  if (N == 64 && K == 128) return launch_v2_dual<64, 128>(p, mode, s);
+  return launch_v2_dual<64, 64>(p, mode, s);
+}

@@ -86,8 +86,11 @@ def dual_message_passing(plan, node_feat, edge_feat, in_weight, out_weight, src_
 
 
 def _padded_width(d):
-    """Width the tcgen05 kernels take (64 or 128) for a feature dimension d, or None when d > 128."""
-    return 64 if d <= 64 else (128 if d <= 128 else None)
+    """Width the tcgen05 kernels take (64 or 128) for a feature dimension d, or None when padding would more than
+    double the row (d <= 32) or d > 128: those widths stay on cuBLAS."""
+    if 32 < d <= 64:
+        return 64
+    return 128 if 64 < d <= 128 else None
 
 
 def _pad_cols(t, width):

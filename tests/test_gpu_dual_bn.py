@@ -1,7 +1,7 @@
 """dmp_gemm_tf32x3_dual (two projections of one streamed operand), dmp_bn_* (BatchNorm1d of the MLPs) and the
 P = NULL form of dmp_edge_update, through the C ABI.
 
-Bars: the dual kernel must equal the two-launch composition it replaces BIT FOR BIT for N = 128 (same MMA sequence per
+Bars: the dual kernel must equal the two-launch composition it replaces BIT FOR BIT (same MMA sequence per
 output element, same epilogue roundings) and stay within the 3xTF32 error bound vs fp64 everywhere; the BatchNorm
 kernels are compared with torch's fp32 batch_norm (forward, running statistics, all gradients) at rtol 1e-5 /
 atol 1e-6 and must be run-to-run bit-stable."""
@@ -29,32 +29,22 @@ def test_dual_store_and_accumulate(M, N, K):
     c = 2 + 6 * torch.rand(M, device="cuda", generator=g)
     ref = A.double() @ W1.double().t() + c.double().unsqueeze(1) * (A.double() @ W2.double().t())
     got = F.gemm_tf32x3_dual(A, W1, W2, row_scale=c, mode="store")
-    assert _err(got, ref) <= 2.5e-6, _err(got, ref)
+    assert _err(got, ref) <= 1.5e-6, _err(got, ref)
     p1, p2 = F.gemm_tf32x3(A, W1), F.gemm_tf32x3(A, W2)
     want = p1 + c.unsqueeze(1) * p2
-    if N == 128:
-        assert torch.equal(got, want)        # same accumulators, same roundings as the two launches it replaces
-    else:
-        torch.testing.assert_close(got, want, rtol=2e-6, atol=2e-6 * float(want.abs().max()))
+    assert torch.equal(got, want)        # same accumulators, same roundings as the two launches it replaces
     # accumulate: (old + acc1) + c * acc2
     D0 = torch.randn(M, N, device="cuda", generator=g)
     D = D0.clone()
     F.gemm_tf32x3_dual(A, W1, W2, row_scale=c, mode="accumulate", out=D)
     want = (D0 + p1) + c.unsqueeze(1) * p2
-    if N == 128:
-        assert torch.equal(D, want)
-    else:
-        torch.testing.assert_close(D, want, rtol=2e-6, atol=2e-6 * float(want.abs().max()))
+    assert torch.equal(D, want)
     # no scale = scale 1
     got1 = F.gemm_tf32x3_dual(A, W1, W2, mode="store")
-    if N == 128:
-        assert torch.equal(got1, p1 + p2)
+    assert torch.equal(got1, p1 + p2)
     # separate outputs
     s1, s2 = F.gemm_tf32x3_dual(A, W1, W2, mode="separate")
-    if N == 128:
-        assert torch.equal(s1, p1) and torch.equal(s2, p2)
-    else:
-        assert _err(s1, A.double() @ W1.double().t()) <= 2.5e-6 and _err(s2, A.double() @ W2.double().t()) <= 2.5e-6
+    assert torch.equal(s1, p1) and torch.equal(s2, p2)
 
 
 def test_dual_strided_operands_and_determinism():
@@ -124,7 +114,7 @@ def test_bn_kernels_match_torch(rows, H, act):
     xr = x.clone().requires_grad_(True)
     gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
     want = torch.nn.functional.batch_norm(xr, None, None, gr, br, True, 0.1, 1e-5)
-    torch.testing.assert_close(got, fn(want).detach(), rtol=1e-5, atol=2e-6)
+    torch.testing.assert_close(got, fn(want).detach(), rtol=1e-5, atol=5e-6)   # |x| up to ~15: 3 ulp
     # backward of the normalisation alone (the activation's derivative rides on the producing GEMM's epilogue)
     if rows > 1:
         want.backward(gy)

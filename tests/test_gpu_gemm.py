@@ -23,7 +23,9 @@ def test_gemm_matches_fp64(M, N, K):
     ref = A.double() @ Wt.double().t()
     got = F.gemm_tf32x3(A, Wt)
     e_ours, e_cublas = _err(got, ref), _err(A @ Wt.t(), ref)
-    assert e_ours <= 2.5e-6, e_ours
+    # cross-terms-first kernel (tf32x3_gemm_v2.cu): the truncating fp32 accumulator of the tensor core
+    # then costs about what an FMA GEMM's rounding costs (model: 6.6e-7 at K = 128)
+    assert e_ours <= 1.0e-6, e_ours
     if M >= 128:  # a single row's sgemm error is luck; compare the two backends on real tiles only
         assert e_ours <= 4 * e_cublas + 5e-7, (e_ours, e_cublas)
 
@@ -58,16 +60,18 @@ def test_gemm_epilogues(act, slope):
     torch.testing.assert_close(got, fn(plain + bias), rtol=1e-6, atol=1e-6)
     # row scale is applied to A as an individually rounded fp32 product
     got = F.gemm_tf32x3(A, Wt, row_scale=scale)
-    assert torch.equal(got, F.gemm_tf32x3(scale.unsqueeze(1) * A, Wt))
+    # (producer-side row scale runs on the interleaved-order kernel, the plain product on the cross-terms-first one:
+    # same value up to the accumulator's truncation pattern)
+    torch.testing.assert_close(got, F.gemm_tf32x3(scale.unsqueeze(1) * A, Wt), rtol=0, atol=2.5e-6 * float(got.abs().max()))
     # accumulate into an existing D
     D0 = torch.randn(M, N, device="cuda", generator=g)
     D = D0.clone()
     F.gemm_tf32x3(A, Wt, out=D, accumulate=True)
     assert torch.equal(D, D0 + plain)
-    # accumulate with a row scale: N = 128 scales the accumulated row (exactly D0 + s * (A W^T)), N = 64 scales A
+    # accumulate with a row scale: the accumulated row is scaled (exactly D0 + s * (A W^T))
     D = D0.clone()
     F.gemm_tf32x3(A, Wt, out=D, accumulate=True, row_scale=scale)
-    want = D0 + scale.unsqueeze(1) * plain if N == 128 else D0 + F.gemm_tf32x3(scale.unsqueeze(1) * A, Wt)
+    want = D0 + scale.unsqueeze(1) * plain
     assert torch.equal(D, want)
     # act'(output) multiply (MLP backward)
     y = fn(torch.randn(M, N, device="cuda", generator=g))
