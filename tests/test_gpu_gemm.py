@@ -168,4 +168,6 @@ def test_gemm_acc_gather_epilogue(N, K, M):
     # no flags / no norm: every edge is a forward edge (sign -1)
     D = D0.clone()
     F.gemm_tf32x3_acc_gather(A, Wt, D, dst32=dst, tab_fwd=t0)
-    assert torch.equal(D, (D0 + F.gemm_tf32x3(A, Wt)) - t0[dst.long()])
+    # (the gather epilogue lives on the round-1 interleaved-order kernel, the plain product on the cross-terms-first one)
+    want = (D0 + F.gemm_tf32x3(A, Wt)) - t0[dst.long()]
+    torch.testing.assert_close(D, want, rtol=0, atol=2.5e-6 * float(want.abs().max()))

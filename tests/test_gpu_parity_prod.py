@@ -68,7 +68,7 @@ def _check(rep, ref64, smooth):
         is_out = k in ("node_out", "edge_out", "rel_pooled")
         scale = float(ref64[k].abs().max())
         if scale < 1e-5:            # exactly 0 in exact arithmetic (bias in front of BatchNorm): rounding noise on both sides
-            assert e["abs_vs_fp64"] <= 1e-4, (k, e)
+            assert e["abs_vs_fp64"] <= 4.0 * e["ref32_abs_vs_fp64"] + 1e-4, (k, e)
             continue
         if is_out or smooth:
             is_wgrad = k.startswith("grad ")
@@ -85,6 +85,7 @@ def _compare(ours, ref32, ref64):
     rep = _parity.compare(ours, ref32, ref64)
     for k, e in rep.items():
         e["abs_vs_fp64"] = float((ours[k].detach().double().cpu() - ref64[k]).abs().max())
+        e["ref32_abs_vs_fp64"] = float((ref32[k].double() - ref64[k]).abs().max())
     return rep
 
 
