@@ -416,6 +416,368 @@ __global__ void __launch_bounds__(kV2Threads, 1) tf32x3_gemm_v2_kernel(const V2P
   if (warp == kV2MmaWarp) tmem_dealloc(tmem_base, kTmemCols);
 }
 
+
+// =====================================================================================================================
+// v3: the same products on 128-ROW tiles.  Measured on this B200 (scripts/micro/mma_rate.cu): a kind::tf32 MMA with
+// M = 128 costs 64 cycles at N = 128 (2048 MAC/clk/SM, the pipe's full rate) but 45 cycles at N = 64 (an issue floor),
+// so the 64-row tiles above pay 1.4x the tensor time per row.  Here N = 128, and cross-terms-first needs the whole K of
+// a 128-row tile resident: 64 KB of raw (= hi) data per tile, so hi and lo live in SEPARATE rings of k-block slots:
+//   hi ring  8 slots x 16 KB (two tiles at K = 128): TMA lands here; a tile's slots are held until its hi*hi pass retires
+//   lo ring  4 slots x 16 KB: written by the producer warps, released k-block by k-block as the cross-term pass retires
+// Warps: 0-7 epilogue, 8 MMA issuer, 9-16 lo producers, 17 TMA issuer (decoupled from the producers so that the loads of
+// tile t+2 start the moment tile t retires).  MMA order per tile: for every k-block [lo*hi, hi*lo] x 4 k-steps (commit
+// frees the lo slot), then for every k-block hi*hi x 4 (one commit frees the tile's hi slots and publishes the
+// accumulator).  Needs TMA (M >= 128); anything else runs the 64-row kernel above.
+constexpr int kV3Rows = 128;
+constexpr int kV3Threads = 18 * 32;
+constexpr int kV3TmaWarp = 17;
+constexpr int kV3LoSlots = 2;
+constexpr int kV3SlotBytes = kV3Rows * 128;         // 16 KB: 128 rows x 32 floats
+constexpr int kV3XchgBytes = 8 * 4096;              // dual: per epilogue warp 32 rows x 32 features
+// 224 KB of tiles either way: the dual forms give two hi slots to the epilogue's exchange buffer
+constexpr int kV3HiSlotsSingle = 12, kV3HiSlotsDual = 10;
+constexpr int kV3Smem = (kV3HiSlotsSingle + kV3LoSlots) * kV3SlotBytes + 512 + 1024;
+static_assert((kV3HiSlotsDual + kV3LoSlots) * kV3SlotBytes + kV3XchgBytes == (kV3HiSlotsSingle + kV3LoSlots) * kV3SlotBytes, "");
+
+template <int NOUT, int K, int MODE>
+__global__ void __launch_bounds__(kV3Threads, 1) tf32x3_gemm_v3_kernel(const V2Params p,
+                                                                       const __grid_constant__ CUtensorMap tmap) {
+  constexpr bool kDual = MODE >= kV2DualStore;
+  constexpr int kKBlocks = K / kKB;                           // k-blocks per tile: 4 or 2
+  constexpr int kV3HiSlots = kDual ? kV3HiSlotsDual : kV3HiSlotsSingle;
+  constexpr int kHalves = kDual ? NOUT / 64 : 1;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sHi = base;
+  const uint32_t sLo = sHi + kV3HiSlots * kV3SlotBytes;
+  const uint32_t sX = sLo + kV3LoSlots * kV3SlotBytes;
+  const uint32_t sBar = sX + (kDual ? kV3XchgBytes : 0);      // both forms: 224 KB of tiles (+ exchange) below the barriers
+  const uint32_t bar_raw = sBar;                              // 12: TMA completion of a hi slot
+  const uint32_t bar_empty_hi = sBar + 96;                    // 12: the tile that used the hi slot has retired
+  const uint32_t bar_full_lo = sBar + 192;                    // 2: lo slot written
+  const uint32_t bar_empty_lo = sBar + 208;                   // 2: cross-term MMAs of the k-block retired
+  const uint32_t bar_acc_full = sBar + 224;                   // 2
+  const uint32_t bar_acc_empty = sBar + 240;                  // 2
+  const uint32_t tmem_slot = sBar + 256;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int fh = (kHalves == 2) ? (int)(blockIdx.x & 1) : 0;
+  const int64_t tile0 = (kHalves == 2) ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x;
+  const int64_t tstep = (kHalves == 2) ? (int64_t)(gridDim.x >> 1) : (int64_t)gridDim.x;
+  const int64_t num_tiles = (p.M + kV3Rows - 1) / kV3Rows;
+  const int64_t my_tiles = tile0 < num_tiles ? (num_tiles - tile0 + tstep - 1) / tstep : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kV3HiSlots; ++s) {
+      mbar_init(bar_raw + 8 * s, 1);
+      mbar_init(bar_empty_hi + 8 * s, 1);
+    }
+    for (int s = 0; s < kV3LoSlots; ++s) {
+      mbar_init(bar_full_lo + 8 * s, kV2ProducerWarps);
+      mbar_init(bar_empty_lo + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_acc_full + 8 * a, 1);
+      mbar_init(bar_acc_empty + 8 * a, kV2EpilogueWarps);
+    }
+    fence_barrier_init();
+  }
+  // TMEM map: [0,128) acc 0 | [128,256) acc 1 | [256,256+K) W hi | [256+K,256+2K) W lo
+  constexpr int kTmemCols = 512;
+  constexpr uint32_t kWhiCol = 256, kWloCol = 256 + K;
+  if (warp == kV2MmaWarp) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  if (warp < 4) {
+    const int l = warp * 32 + lane;
+    const float* wrow;
+    if constexpr (kDual) wrow = ((l < 64) ? p.W1 : p.W2) + (int64_t)(fh * 64 + (l & 63)) * p.ldw;
+    else wrow = p.W1 + (int64_t)(l < NOUT ? l : 0) * p.ldw;
+    const bool zero_row = !kDual && l >= NOUT;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+    for (int c0 = 0; c0 < K; c0 += 32) {
+      float hi[32], lo[32];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float4 v = __ldg(reinterpret_cast<const float4*>(wrow + c0 + 4 * q));
+        if (zero_row) v = make_float4(0.f, 0.f, 0.f, 0.f);
+        hi[4 * q + 0] = tf32_rna(v.x); lo[4 * q + 0] = __fsub_rn(v.x, hi[4 * q + 0]);
+        hi[4 * q + 1] = tf32_rna(v.y); lo[4 * q + 1] = __fsub_rn(v.y, hi[4 * q + 1]);
+        hi[4 * q + 2] = tf32_rna(v.z); lo[4 * q + 2] = __fsub_rn(v.z, hi[4 * q + 2]);
+        hi[4 * q + 3] = tf32_rna(v.w); lo[4 * q + 3] = __fsub_rn(v.w, hi[4 * q + 3]);
+      }
+      tmem_st32(t_lane + kWhiCol + c0, hi);
+      tmem_st32(t_lane + kWloCol + c0, lo);
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (warp == kV3TmaWarp) {
+    // =========================== TMA ISSUER ===========================
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t sphase = 0;
+#pragma unroll 1
+      for (int64_t t = 0; t < my_tiles; ++t) {
+        const int r0 = (int)((tile0 + t * tstep) * kV3Rows);
+#pragma unroll 1
+        for (int kb = 0; kb < kKBlocks; ++kb) {
+          mbar_wait(bar_empty_hi + 8 * slot, sphase ^ 1);       // the slot's previous tile has retired
+          mbar_expect_tx(bar_raw + 8 * slot, kV3SlotBytes);
+          tma_load_2d(sHi + slot * kV3SlotBytes, &tmap, kb * kKB, r0, bar_raw + 8 * slot);
+          if (++slot == kV3HiSlots) { slot = 0; sphase ^= 1; }
+        }
+      }
+    }
+  } else if (warp > kV2MmaWarp) {
+    // =========================== LO PRODUCERS ===========================
+    const int pt = threadIdx.x - (kV2MmaWarp + 1) * 32;        // 0..255
+    const int c16 = pt & 7;
+    const int row0 = pt >> 3;                                   // rows row0 + 32 i
+    uint32_t offs[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) offs[i] = swz(row0 + 32 * i, c16);
+    int hs = 0, ls = 0;
+    uint32_t hphase = 0, lphase = 0;
+#pragma unroll 1
+    for (int64_t g = 0; g < my_tiles * kKBlocks; ++g) {
+      mbar_wait(bar_raw + 8 * hs, hphase);                      // the raw k-block has landed
+      mbar_wait(bar_empty_lo + 8 * ls, lphase ^ 1);             // the lo slot's previous user has retired
+      const uint32_t hi = sHi + hs * kV3SlotBytes, lo = sLo + ls * kV3SlotBytes;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 v = lds128(hi + offs[i]);
+        sts128(lo + offs[i], make_float4(tf32_trunc_residual(v.x), tf32_trunc_residual(v.y), tf32_trunc_residual(v.z),
+                                         tf32_trunc_residual(v.w)));
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_full_lo + 8 * ls);
+      if (++hs == kV3HiSlots) { hs = 0; hphase ^= 1; }
+      if (++ls == kV3LoSlots) { ls = 0; lphase ^= 1; }
+    }
+  } else if (warp == kV2MmaWarp) {
+    // =========================== MMA ISSUER ===========================
+    constexpr uint32_t idesc = make_idesc(128, kV3Rows);
+    int acc = 0, ls = 0, hs0 = 0;                              // hs0: hi slot of the tile's first k-block
+    uint32_t acc_phase = 0, lphase = 0;
+#pragma unroll 1
+    for (int64_t t = 0; t < my_tiles; ++t) {
+      mbar_wait(bar_acc_empty + 8 * acc, acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kV3Rows);
+      // pass 1: cross terms, k-block by k-block (the accumulator is still small: truncation costs 2^-11 of what it
+      // would cost after the hi*hi terms)
+#pragma unroll
+      for (int kb = 0; kb < kKBlocks; ++kb) {
+        mbar_wait(bar_full_lo + 8 * ls, lphase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_hi = sHi + ((hs0 + kb) % kV3HiSlots) * kV3SlotBytes;
+          const uint32_t a_lo = sLo + ls * kV3SlotBytes;
+#pragma unroll
+          for (int j = 0; j < kKB / 8; ++j) {
+            const uint64_t dah = make_smem_desc(a_hi + j * 32);
+            const uint64_t dal = make_smem_desc(a_lo + j * 32);
+            const uint32_t w_hi = tmem_base + kWhiCol + (uint32_t)(kb * kKB + j * 8);
+            const uint32_t w_lo = tmem_base + kWloCol + (uint32_t)(kb * kKB + j * 8);
+            umma_tf32_ts(d_tmem, w_hi, dal, idesc, (kb | j) != 0 ? 1u : 0u);
+            umma_tf32_ts(d_tmem, w_lo, dah, idesc, 1u);
+          }
+          umma_commit(bar_empty_lo + 8 * ls);
+        }
+        __syncwarp();
+        if (++ls == kV3LoSlots) { ls = 0; lphase ^= 1; }
+      }
+      // pass 2: the dominant hi*hi terms
+      if (lane == 0) {
+#pragma unroll
+        for (int kb = 0; kb < kKBlocks; ++kb) {
+          const uint32_t a_hi = sHi + ((hs0 + kb) % kV3HiSlots) * kV3SlotBytes;
+#pragma unroll
+          for (int j = 0; j < kKB / 8; ++j) {
+            const uint64_t dah = make_smem_desc(a_hi + j * 32);
+            const uint32_t w_hi = tmem_base + kWhiCol + (uint32_t)(kb * kKB + j * 8);
+            umma_tf32_ts(d_tmem, w_hi, dah, idesc, 1u);
+          }
+        }
+#pragma unroll
+        for (int kb = 0; kb < kKBlocks; ++kb) umma_commit(bar_empty_hi + 8 * ((hs0 + kb) % kV3HiSlots));
+        umma_commit(bar_acc_full + 8 * acc);
+      }
+      __syncwarp();
+      hs0 = (hs0 + kKBlocks) % kV3HiSlots;
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // =========================== EPILOGUE ===========================
+    const int quad = warp & 3, half = warp >> 2;     // TMEM lane quadrant, row half (64 rows)
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    if constexpr (!kDual) {
+      constexpr bool kNeedAux = (MODE == kV2GradPwl || MODE == kV2GradSmooth);
+      constexpr bool kNeedBias = (MODE == kV2BiasPwl || MODE == kV2BiasSmooth);
+      constexpr bool kNeedOld = (MODE == kV2Accumulate || MODE == kV2AccumulateScaled);
+      constexpr bool kScaled = (MODE == kV2AccumulateScaled);
+      const int f = quad * 32 + lane;
+      const bool live = quad * 32 < NOUT;
+      const float bias_f = (kNeedBias && live && p.bias != nullptr) ? __ldg(p.bias + f) : 0.0f;
+#pragma unroll 1
+      for (int64_t t = 0; t < my_tiles; ++t) {
+        if (!live) {
+          mbar_wait(bar_acc_full + 8 * acc, acc_phase);
+          if (lane == 0) mbar_arrive(bar_acc_empty + 8 * acc);
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+          continue;
+        }
+        const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kV3Rows + half * 64);
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          const int64_t r0 = (tile0 + t * tstep) * kV3Rows + half * 64 + c * 32;
+          const int nvalid = (int)((p.M - r0) < 32 ? (p.M - r0) : 32);     // warp-uniform, may be <= 0
+          float* dst = p.D + r0 * p.ldd + f;
+          float tt[32];
+          if constexpr (kNeedAux || kNeedOld) {
+            // streamed epilogue operand of the chunk requested before the accumulator is touched (first chunk: before
+            // waiting for this tile's MMAs, so its DRAM latency hides behind them)
+            const float* src = kNeedAux ? p.aux + r0 * p.ld_aux + f : dst;
+            const int64_t lds = kNeedAux ? p.ld_aux : p.ldd;
+            if (nvalid == 32) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) tt[j] = src[j * lds];
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) tt[j] = j < nvalid ? src[j * lds] : 0.0f;
+            }
+          }
+          float sc_l = 1.0f;
+          if (kScaled && lane < nvalid) sc_l = __ldg(p.scale + r0 + lane);
+          if (c == 0) {
+            mbar_wait(bar_acc_full + 8 * acc, acc_phase);
+            tc_fence_after();
+          }
+          float v[32];
+          tmem_ld32(t_lane + c * 32, v);
+          if (c == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_acc_empty + 8 * acc);
+          }
+          asm volatile("" : "+l"(dst));      // accumulate: do not keep the 32 load addresses alive for the stores
+          if constexpr (kScaled) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __fmul_rn(__shfl_sync(0xffffffffu, sc_l, j), v[j]);
+          }
+          if (nvalid == 32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              dst[j * p.ldd] = v2_epilogue_op<MODE>(v[j], bias_f, kNeedAux ? tt[j] : 0.0f, kNeedOld ? tt[j] : 0.0f, p.slope, p.act);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nvalid)
+                dst[j * p.ldd] = v2_epilogue_op<MODE>(v[j], bias_f, kNeedAux ? tt[j] : 0.0f, kNeedOld ? tt[j] : 0.0f, p.slope, p.act);
+          }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    } else {
+      const int which = quad >> 1;
+      const int f = fh * 64 + (quad & 1) * 32 + lane;
+      const uint32_t my_x = sX + (uint32_t)warp * 4096u + (uint32_t)lane * 4u;
+      const uint32_t peer_x = sX + (uint32_t)(warp ^ 2) * 4096u + (uint32_t)lane * 4u;
+      const int bar_id = 1 + (quad & 1) * 2 + half;
+#pragma unroll 1
+      for (int64_t t = 0; t < my_tiles; ++t) {
+        const int64_t rt = (tile0 + t * tstep) * kV3Rows + half * 64;     // first of this warp's 64 rows
+        const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kV3Rows + half * 64);
+        if constexpr (MODE == kV2DualSeparate) {
+          mbar_wait(bar_acc_full + 8 * acc, acc_phase);
+          tc_fence_after();
+          float* out = which ? p.D2 : p.D;
+          const int64_t ldo = which ? p.ldd2 : p.ldd;
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            float v[32];
+            tmem_ld32(t_lane + c * 32, v);
+            if (c == 1) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar_acc_empty + 8 * acc);
+            }
+            const int64_t r0 = rt + c * 32;
+            float* dst = out + r0 * ldo + f;
+            const int nvalid = (int)((p.M - r0) < 32 ? (p.M - r0) : 32);
+            if (nvalid == 32) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) dst[j * ldo] = v[j];
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nvalid) dst[j * ldo] = v[j];
+            }
+          }
+        } else {
+          // rows this warp finalises: 32 rows starting at r0 (acc1 warp: the first 32 of the pair's 64, acc2 warp: the rest)
+          const int64_t r0 = rt + which * 32;
+          const int nvalid = (int)((p.M - r0) < 32 ? (p.M - r0) : 32);     // warp-uniform, may be <= 0
+          float* dst = p.D + r0 * p.ldd + f;
+          float old[32];
+          if constexpr (MODE == kV2DualAccumulate) {
+            if (nvalid == 32) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) old[j] = dst[j * p.ldd];
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) old[j] = j < nvalid ? dst[j * p.ldd] : 0.0f;
+            }
+          }
+          float sc_l = 1.0f;
+          if (p.scale != nullptr && lane < nvalid) sc_l = __ldg(p.scale + r0 + lane);
+          mbar_wait(bar_acc_full + 8 * acc, acc_phase);
+          tc_fence_after();
+          asm volatile("" : "+l"(dst));
+          // the partner has finished reading what I wrote for the previous tile
+          asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+          float v[32];
+          tmem_ld32(t_lane + (which ? 0 : 32), v);                  // the rows the partner finalises
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(my_x + j * 128), "f"(v[j]) : "memory");
+          tmem_ld32(t_lane + (which ? 32 : 0), v);                  // the rows this warp finalises
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_acc_empty + 8 * acc);
+          asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float got = lds32(peer_x + j * 128);
+            const float a1 = which ? got : v[j];
+            const float a2 = which ? v[j] : got;
+            const float c = __shfl_sync(0xffffffffu, sc_l, j);
+            float r = (MODE == kV2DualAccumulate) ? __fadd_rn(old[j], a1) : a1;
+            r = __fadd_rn(r, __fmul_rn(c, a2));
+            if (j < nvalid) dst[j * p.ldd] = r;
+          }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kV2MmaWarp) tmem_dealloc(tmem_base, kTmemCols);
+}
+
 // TMA descriptor of the streamed operand: fp32 [M rows x K], box = 64 rows x 32 floats, 128-byte swizzle
 static bool make_tmap_rows64(CUtensorMap* tmap, const float* A, int64_t lda, int64_t M, int K) {
   TmapEncodeFn enc = tmap_encoder();
@@ -429,9 +791,36 @@ static bool make_tmap_rows64(CUtensorMap* tmap, const float* A, int64_t lda, int
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+static bool v3_enabled() {   // DMP_GEMM_V3=0: 64-row kernel everywhere (A/B runs)
+  static const bool on = [] { const char* e = getenv("DMP_GEMM_V3"); return e ? atoi(e) != 0 : true; }();
+  return on;
+}
+
 template <int NOUT, int K, int MODE>
 static int launch_v2_mode(const V2Params& p, cudaStream_t stream) {
   using L = V2Smem<K>;
+  constexpr int kHalves = (MODE >= kV2DualStore) ? NOUT / 64 : 1;
+  const int64_t streams = kNumSMs / kHalves;
+  V2Params q = p;
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  if (v3_enabled() && tma_enabled() && p.M >= kV3Rows && make_tmap_rows(&tmap, p.A, p.lda, p.M, K)) {
+    static bool configured3 = false;
+    if (!configured3) {
+      cudaError_t e = cudaFuncSetAttribute(tf32x3_gemm_v3_kernel<NOUT, K, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           kV3Smem);
+      if (e != cudaSuccess) {
+        set_error("gemm_tf32x3 (v3): cannot reserve %d bytes of shared memory: %s", kV3Smem, cudaGetErrorString(e));
+        return DMP_ERR_CUDA;
+      }
+      configured3 = true;
+    }
+    const int64_t tiles = (p.M + kV3Rows - 1) / kV3Rows;
+    const unsigned grid = (unsigned)((tiles < streams ? tiles : streams) * kHalves);
+    q.use_tma = 1;
+    tf32x3_gemm_v3_kernel<NOUT, K, MODE><<<grid, kV3Threads, kV3Smem, stream>>>(q, tmap);
+    return launch_status("tf32x3_gemm_v3_kernel");
+  }
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(tf32x3_gemm_v2_kernel<NOUT, K, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -442,13 +831,8 @@ static int launch_v2_mode(const V2Params& p, cudaStream_t stream) {
     }
     configured = true;
   }
-  constexpr int kHalves = (MODE >= kV2DualStore) ? NOUT / 64 : 1;
   const int64_t tiles = (p.M + kV2Rows - 1) / kV2Rows;
-  const int64_t streams = kNumSMs / kHalves;
   const unsigned grid = (unsigned)((tiles < streams ? tiles : streams) * kHalves);
-  V2Params q = p;
-  CUtensorMap tmap;
-  memset(&tmap, 0, sizeof(tmap));
   q.use_tma = (tma_enabled() && p.M >= kV2Rows && make_tmap_rows64(&tmap, p.A, p.lda, p.M, K)) ? 1 : 0;
   tf32x3_gemm_v2_kernel<NOUT, K, MODE><<<grid, kV2Threads, L::kTotal, stream>>>(q, tmap);
   return launch_status("tf32x3_gemm_v2_kernel");
