@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- DMPNN layer forward+backward throughput on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg5|cfg4|cfg2]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|reference_gpu] [--workload cfg5|cfg2]
 
 One "step" = one DMPLayer (hidden 128, 2-layer MLPs, leaky_relu; the SubgraphCountingMatching default
 layer) forward + backward over the whole synthetic graph through the module API
@@ -19,7 +19,13 @@ N > 1: the graph is partitioned by destination-node range (edges live with their
 states are all-gathered forward and their gradients reduce-scattered backward (parallel.py); value is
 total edges of the whole graph / max-over-ranks step time ("strong" scaling: total work is fixed).
 
-`--impl reference` times the reference's CPU path (oracle restatement, DGL unavailable offline) only.
+`--impl reference` times the reference's CPU path (oracle restatement, DGL unavailable offline) only;
+`--impl reference_gpu` times the reference's op sequence as eager torch ops on the GPU (what DGL's UDF path launches).
+
+Also in the line: `parity` (our layer vs the CPU oracle on the cpu_baseline sample: strict elementwise violation
+fraction + max-norm error), `gpu_baseline` (eager-torch GPU comparator), `cfg4` (BASELINE configs[3]: the UNC encoder
+body, 2 x DualGraphConv with BatchNorm + relation pooling, H = 50), `mlp0`, `train` (configs[0..2] pairs/s) and, at
+N > 1, `multi_gpu_parity` (partitioned vs single-GPU layer on a mini graph, checked before timing).
 """
 import argparse
 import json
@@ -42,7 +48,6 @@ WORKLOADS = {
     "cfg5": (2_000_000, 20_000_000, 128,
              "BASELINE configs[4]: single ER graph 2M nodes / 40M edges (20M + reversed), hidden 128, "
              "DMPLayer mlp=2 leaky_relu fwd+bwd"),
-    "cfg4": (20_000, 90_000, 128, "BASELINE configs[3]-sized: 20k nodes / 180k edges, hidden 128"),
     "cfg2": (20_480, 81_920, 64, "BASELINE configs[1] graph side: ~20k nodes / 164k edges, hidden 64"),
 }
 METRIC = "DMPNN layer fwd+bwd edges/sec"
@@ -54,14 +59,16 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference_gpu"])
     ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS))
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the secondary train graphs/sec measurement")
     ap.add_argument("--no-mlp0", action="store_true", help="skip the num_mlp_layers=0 variant of the layer")
-    ap.add_argument("--train-config", default="cfg2", choices=["cfg1", "cfg2", "cfg3"])
+    ap.add_argument("--train-config", default="all", choices=["all", "cfg1", "cfg2", "cfg3"])
+    ap.add_argument("--no-cfg4", action="store_true", help="skip the UNC encoder (BASELINE configs[3]) measurement")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the eager-torch GPU comparator")
     ap.add_argument("--train-steps", type=int, default=30)
     ap.add_argument("--cpu-sample-edges", type=int, default=0, help="override the CPU sample size (edges incl. reversed)")
     return ap.parse_args()
@@ -82,7 +89,9 @@ def make_graph(n, e0, seed):
 
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle restatement of the reference layer on host cores
-def cpu_reference_step_fn(n, e0, h, seed):
+def cpu_reference_step_fn(n, e0, h, seed, keep=None):
+    """One fwd+bwd of the CPU oracle (reference op order).  `keep` (dict) receives the inputs, parameters, outputs and
+    input gradients of the last step -- the checker side of the `parity` object."""
     from oracle import dmp_oracle  # the ONLY use of oracle/ in this file: the thing being compared against
     import dualmessagepassing_b200 as dmp
     src, dst, rev = make_graph(n, e0, seed)
@@ -100,9 +109,109 @@ def cpu_reference_step_fn(n, e0, h, seed):
             t.grad = None
         nv, ne = dmp_oracle.dmp_layer(P, s, d, n, xv, xe, rev=r, flavour="scm", act_func="leaky_relu")
         torch.autograd.backward((nv, ne), (gv, ge))
+        if keep is not None:
+            keep.update(src=src, dst=dst, rev=rev, n=n, state={k: v.detach().clone() for k, v in P.items()},
+                        xv=xv.detach(), xe=xe.detach(), gv=gv, ge=ge,
+                        ref={"node_out": nv.detach(), "edge_out": ne.detach(), "grad_node_feat": xv.grad.clone(),
+                             "grad_edge_feat": xe.grad.clone()})
         return float(nv[0, 0].detach())
 
     return step, E
+
+
+def parity_on_sample(keep, h, dev):
+    """Our layer (module API, production dispatch) on the cpu_baseline sample vs the oracle's fp32 result of the same
+    inputs: the strict elementwise form |a-b| <= 1e-6 + 1e-5|b| as a violation fraction, and max-norm relative error.
+    Input gradients run through leaky_relu: a pre-activation at rounding distance from 0 flips act' between two valid
+    fp32 evaluations (the reference-order oracle shows the same against fp64, tests/test_gpu_parity_prod.py), so their
+    max-norm figure is flip noise, reported as such."""
+    import dualmessagepassing_b200 as dmp
+    from dualmessagepassing_b200.constants import REVFLAG
+    from tests import _parity
+    layer = dmp.DMPLayer(h, h, num_mlp_layers=2, batch_norm=False, act_func="leaky_relu")
+    layer.load_state_dict(keep["state"])
+    layer.to(dev)
+    g = dmp.DMPGraph(torch.from_numpy(keep["src"]), torch.from_numpy(keep["dst"]), keep["n"]).to(dev)
+    g.edata[REVFLAG] = torch.from_numpy(keep["rev"]).to(dev).bool()
+    g.rev_layout_hint = "halves"
+    a, b = keep["xv"].to(dev).requires_grad_(True), keep["xe"].to(dev).requires_grad_(True)
+    nv, ne = layer(g, a, b)
+    torch.autograd.backward((nv, ne), (keep["gv"].to(dev), keep["ge"].to(dev)))
+    ours = {"node_out": nv, "edge_out": ne, "grad_node_feat": a.grad, "grad_edge_feat": b.grad}
+    rep = _parity.compare(ours, keep["ref"])
+    fwd = {k: rep[k] for k in ("node_out", "edge_out")}
+    bwd = {k: rep[k] for k in ("grad_node_feat", "grad_edge_feat")}
+    ok = all(e["maxrel_vs_ref32"] <= 1e-5 for e in fwd.values())
+    return {"against": "oracle/dmp_oracle.py fp32 (reference op order) on the cpu_baseline sample",
+            "tolerance": "strict elementwise |a-b| <= 1e-6 + 1e-5|b| (violation fraction) and max-norm relative error",
+            "forward": _parity.summarise(fwd), "input_grads": _parity.summarise(bwd),
+            "input_grads_note": "through leaky_relu: dominated by act' flips at pre-activations within rounding of 0",
+            "ok": bool(ok), "yardstick": "tests/test_gpu_parity_prod.py: reference-order fp32 vs fp64 on the same shapes"}
+
+
+def eager_gpu_step_fn(n, e0, h, seed, dev):
+    """The reference's own op sequence (dmpnn.py:111-156) as eager torch ops on CUDA tensors: both branches computed and
+    masked_fill-ed, per-edge gathers, index_add_ for fn.sum, nn.Sequential MLPs, autograd backward -- what DGL's UDF
+    path launches on a GPU (none of this repo's kernels)."""
+    import dualmessagepassing_b200 as dmp
+    src, dst, rev = make_graph(n, e0, seed)
+    torch.manual_seed(seed)
+    layer = dmp.DMPLayer(h, h, num_mlp_layers=2, batch_norm=False, act_func="leaky_relu").to(dev)
+    E = 2 * e0
+    gen = torch.Generator(device=dev).manual_seed(seed)
+    xv = torch.randn(n, h, device=dev, generator=gen, requires_grad=True)
+    xe = torch.randn(E, h, device=dev, generator=gen, requires_grad=True)
+    gv, ge = torch.randn(n, h, device=dev, generator=gen), torch.randn(E, h, device=dev, generator=gen)
+    s, d = torch.from_numpy(src).to(dev), torch.from_numpy(dst).to(dev)
+    rmask = torch.from_numpy(rev.astype(bool)).to(dev).view(-1, 1)
+    mask = ~rmask
+    out_deg = torch.bincount(s, minlength=n)
+    L = layer
+
+    def step():
+        for t in list(L.parameters()) + [xv, xe]:
+            t.grad = None
+        hs, hd = xv[s], xv[d]
+        edge_msg = hd @ L.dst_weight - hs @ L.src_weight
+        node_msg = -(xe @ L.in_weight)
+        rev_edge_msg = hs @ L.dst_weight - hd @ L.src_weight
+        rev_node_msg = xe @ L.out_weight
+        edge_msg = edge_msg.masked_fill(rmask, 0.0) + rev_edge_msg.masked_fill(mask, 0.0)
+        node_msg = node_msg.masked_fill(rmask, 0.0) + rev_node_msg.masked_fill(mask, 0.0)
+        node_agg = torch.zeros((n, h), device=dev).index_add_(0, d, node_msg)
+        node_pre = xv @ L.nloop_weight + node_agg + L.nbias
+        dd = (1 + out_deg[d].unsqueeze(-1).float()).log2()
+        add = 2 * (1 + dd) * (xe @ (L.src_weight - L.dst_weight))
+        edge_pre = xe @ L.eloop_weight + add + edge_msg + L.ebias
+        nv, ne = L.nmlp(node_pre), L.emlp(edge_pre)
+        torch.autograd.backward((nv, ne), (gv, ge))
+
+    return step, E
+
+
+def run_gpu_baseline(n, e0, h, dev, steps=3):
+    """edges/s of the eager-torch comparator at the largest 1/k scale of the workload whose ~25 live [E,H] temporaries
+    fit beside nothing else (1/10 for cfg5)."""
+    free = torch.cuda.mem_get_info(dev)[0]
+    scale = 1
+    while 30 * (2 * e0 // scale) * h * 4 > free * 0.8:
+        scale += 1
+    sn, se0 = max(1000, n // scale), max(1000, e0 // scale)
+    step, E = eager_gpu_step_fn(sn, se0, h, 5000, dev)
+    step()
+    torch.cuda.synchronize()
+    e0_, e1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0_.record()
+    for _ in range(steps):
+        step()
+    e1_.record()
+    torch.cuda.synchronize()
+    ms = e0_.elapsed_time(e1_) / steps
+    del step
+    torch.cuda.empty_cache()
+    return {"value": E / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "kind": "reference op sequence as eager torch ops "
+            "on the GPU (index_select / masked_fill / index_add_ / cuBLAS sgemm / autograd): what DGL's UDF path launches",
+            "sample": "1/%d-scale: %d nodes, %d edges (incl. reversed), H=%d" % (scale, sn, E, h), "steps": steps}
 
 
 def cpu_sample_shape(n, e0, budget_s):
@@ -117,8 +226,7 @@ def run_reference(args):
     n, e0, h, desc = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    total = args.steps + args.warmup
-    sn, se0 = cpu_sample_shape(n, e0, budget_s=max(2.0, 150.0 / max(total, 1)))
+    sn, se0 = cpu_sample_shape(n, e0, budget_s=10.0)   # the SAME sample as the cpu_baseline leg of the other arm
     if args.cpu_sample_edges:
         se0 = args.cpu_sample_edges // 2
         sn = max(1000, int(n * se0 / e0))
@@ -141,6 +249,143 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def run_reference_gpu(args):
+    """`--impl reference_gpu`: the eager-torch comparator alone, same JSON shape as the reference arm."""
+    n, e0, h, desc = WORKLOADS[args.workload]
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    gb = run_gpu_baseline(n, e0, h, dev, steps=max(args.steps, 1))
+    line = {"impl": "reference_gpu", "metric": METRIC, "value": gb["value"], "unit": UNIT, "n_gpus": 1,
+            "steps": args.steps, "warmup": 1, "ms_per_step": gb["ms_per_step"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "reference_impl": gb["kind"], "sample": gb["sample"]},
+            "gpu_baseline": gb}
+    print(json.dumps(line), flush=True)
+
+
+def run_cfg4(dev, hbm_peak, steps=20):
+    """BASELINE configs[3]: the UNC encoder body as the reference runs it (model.py:299-328) -- one graph from
+    `build_graph_from_triplets`(20 k nodes, 90 k triplets, 10 relations -> 180 k edges, norm = 1/in-degree), 2 x
+    DualGraphConv (BatchNorm MLP; Tanh, then none), relation mean pooling; hidden 50 (UNC/run.sh), full-graph fwd+bwd.
+    Every operand fits L2 (46 MB per [E,64] matrix), so L2 is flushed (256 MB write) before every timed step."""
+    import dualmessagepassing_b200 as dmp
+    from dualmessagepassing_b200 import _lib
+    n, nt, R, h = 20_000, 90_000, 10, 50
+    rng = np.random.Generator(np.random.PCG64(4000))
+    trip = np.stack([rng.integers(0, n, nt), rng.integers(0, R, nt), rng.integers(0, n, nt)], 1)
+    g = dmp.build_graph_from_triplets(n, R, trip).to(dev)
+    E = g.number_of_edges()
+    torch.manual_seed(4000)
+    layers = [dmp.DualGraphConv(h, h, activation=torch.nn.Tanh()).to(dev).train(),
+              dmp.DualGraphConv(h, h, activation=None).to(dev).train()]
+    gen = torch.Generator(device=dev).manual_seed(4000)
+    h0, z0 = torch.randn(n, h, device=dev, generator=gen), torch.randn(E, h, device=dev, generator=gen)
+    gh, gz = torch.randn(n, h, device=dev, generator=gen), torch.randn(E, h, device=dev, generator=gen)
+    gr = torch.randn(2 * R, h, device=dev, generator=gen)
+    params = [p for L in layers for p in L.parameters()]
+
+    def step():
+        for p in params:
+            p.grad = None
+        a, b = h0.requires_grad_(True), z0.requires_grad_(True)
+        x, y = a, b
+        for L in layers:
+            x, y = L(g, x, y, g.edata["norm"])
+        pooled = dmp.relation_mean_pool(y, g.edata["type"], 2 * R)
+        torch.autograd.backward((x, y, pooled), (gh, gz, gr))
+        a.grad = b.grad = None
+
+    for _ in range(5):
+        step()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    evs = []
+    l0 = _lib.LAUNCHES
+    for _ in range(steps):
+        flush.zero_()
+        e0_, e1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0_.record()
+        step()
+        e1_.record()
+        evs.append((e0_, e1_))
+    torch.cuda.synchronize()
+    launches = (_lib.LAUNCHES - l0) / steps
+    ms = float(np.median([a.elapsed_time(b) for a, b in evs]))
+    # one profiled step: which hand-written kernels ran, and the bytes the GEMM launches report
+    _lib.PROFILE = []
+    step()
+    torch.cuda.synchronize()
+    prof, _lib.PROFILE = _lib.PROFILE, None
+    tags = {}
+    for tag, a, b, nb in prof:
+        t = tags.setdefault(tag, [0, 0.0, 0])
+        t[0] += 1
+        t[1] += a.elapsed_time(b)
+        t[2] += nb or 0
+    # SURVEY 8(d): sparse-core algorithmic bytes per layer fwd+bwd, plus the dense launches' own operand bytes
+    idx_bytes = 17 * E + 12 * (n + 1)
+    sparse = 2 * (4 * h * (9 * E + 4 * n) + 2 * idx_bytes)
+    dense = sum(v[2] for k, v in tags.items() if k.startswith(("gemm", "bn_")))
+    return {"workload": "BASELINE configs[3]: UNC encoder body, 20k nodes / 90k triplets -> %d edges, 2 x DualGraphConv("
+                        "BatchNorm, Tanh/None) + relation mean pooling, hidden %d (zero-padded to 64 for the tcgen05 "
+                        "kernels), full-graph fwd+bwd" % (E, h),
+            "ms_per_step": ms, "value": 2 * E / (ms * 1e-3), "unit": "edges/s (edges x layers per second)",
+            "steps": steps, "l2": "L2 flushed (256 MB write) before every timed step; median of per-step CUDA-event times",
+            "dmp_launches_per_step": launches,
+            "hbm": {"sparse_core_alg_bytes": sparse, "dense_launch_bytes": dense,
+                    "frac": (sparse + dense) / (ms * 1e-3) / 1e9 / hbm_peak,
+                    "note": "launch-latency regime: %d launches of ~10-30 us kernels per step" % round(launches)},
+            "kernels": {k: {"launches": v[0], "ms": v[1]} for k, v in sorted(tags.items(), key=lambda kv: -kv[1][1])}}
+
+
+def multi_gpu_parity(rank, world, dev):
+    """Partitioned layer (all-gather / reduce-scatter / all-reduce over NCCL) vs the single-GPU layer on a mini graph,
+    BEFORE anything is timed: max-norm relative difference over outputs, input gradients and weight gradients, max over
+    ranks.  The partition keeps the single-GPU summation order, so this is rounding-level (GEMM tile boundaries move)."""
+    import torch.distributed as dist
+    import dualmessagepassing_b200 as dmp
+    from dualmessagepassing_b200.constants import REVFLAG
+    from dualmessagepassing_b200.parallel import PartitionedDMPLayer
+    n, e0, h = 64_000, 640_000, 128
+    src, dst, rev = make_graph(n, e0, seed=77)
+    E = 2 * e0
+    torch.manual_seed(77)
+    layer = dmp.DMPLayer(h, h, num_mlp_layers=2, batch_norm=False, act_func="tanh").to(dev)   # smooth: no act' flips
+    gen = torch.Generator(device=dev).manual_seed(78)                                          # same on every rank
+    xv, xe = torch.randn(n, h, device=dev, generator=gen), torch.randn(E, h, device=dev, generator=gen)
+    gv, ge = torch.randn(n, h, device=dev, generator=gen), torch.randn(E, h, device=dev, generator=gen)
+    graph = dmp.DMPGraph(torch.from_numpy(src), torch.from_numpy(dst), n).to(dev)
+    graph.edata[REVFLAG] = torch.from_numpy(rev).to(dev).bool()
+    a, b = xv.clone().requires_grad_(True), xe.clone().requires_grad_(True)
+    nv, ne = layer(graph, a, b)
+    torch.autograd.backward((nv, ne), (gv, ge))
+    ref_w = {k: p.grad.clone() for k, p in layer.named_parameters()}
+    layer.zero_grad()
+    runner = PartitionedDMPLayer(layer, src, dst, rev, n, rank, world, dev)
+    lo, hi = runner.n_lo, min(runner.n_hi, n)
+    ids = torch.from_numpy(runner.part["eids"]).to(dev)
+    pad = runner.local_N - (hi - lo)
+    xv_l = torch.nn.functional.pad(xv[lo:hi], (0, 0, 0, pad)) if pad else xv[lo:hi]
+    a2, b2 = xv_l.clone().requires_grad_(True), xe[ids].clone().requires_grad_(True)
+    nv2, ne2 = runner(a2, b2)
+    gv_l = torch.nn.functional.pad(gv[lo:hi], (0, 0, 0, pad)) if pad else gv[lo:hi]
+    torch.autograd.backward((nv2, ne2), (gv_l, ge[ids]))
+
+    def rel(x, y):
+        return float((x - y).abs().max() / y.abs().max().clamp_min(1e-30))
+
+    errs = {"node_out": rel(nv2[:hi - lo], nv[lo:hi]), "edge_out": rel(ne2, ne[ids]),
+            "grad_node_feat": rel(a2.grad[:hi - lo], a.grad[lo:hi]), "grad_edge_feat": rel(b2.grad, b.grad[ids]),
+            "weight_grads": max(rel(p.grad, ref_w[k]) for k, p in layer.named_parameters())}
+    t = torch.tensor([errs[k] for k in sorted(errs)], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    errs = dict(zip(sorted(errs), [float(x) for x in t.tolist()]))
+    del runner, graph
+    torch.cuda.empty_cache()
+    return {"max_rel": max(errs.values()), "per_tensor": errs, "ok": bool(max(errs.values()) <= 2e-5),
+            "what": "PartitionedDMPLayer vs DMPLayer on one %d-node / %d-edge graph, H=%d, tanh, world=%d (max over ranks)"
+                    % (n, E, h, world)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -190,8 +435,9 @@ def kernel_bytes(tag, N, E, H, has_norm=False, mirrored=False):
     if tag.startswith("segment_reduce"):
         return E * row + N * row + 4 * E + 4 * (N + 1)
     if tag == "edge_update":
-        # S, P, out per edge + the two endpoint rows: fetched once per mirrored PAIR of edges (e, e + E/2) on one graph
-        return (4 if mirrored else 5) * E * row + 12 * E + row
+        # U (= S + coef*P, written by the dual projection), out per edge + the two endpoint rows: fetched once per mirrored
+        # PAIR of edges (e, e + E/2) on one graph
+        return (3 if mirrored else 4) * E * row + 12 * E + row
     if tag == "edge_backward":
         return 2 * E * row + 5 * E   # gather gN[dst] + write T (coef*gE is folded into the GEMM prologues)
     if tag == "act_inplace":
@@ -199,31 +445,39 @@ def kernel_bytes(tag, N, E, H, has_norm=False, mirrored=False):
     return None
 
 
-def run_train(args, dev, world, rank):
-    """Secondary metric of BASELINE.json: end-to-end training graphs/sec on configs[1] (batch 512 pairs per
-    GPU, data parallel).  Every timed step = host collate of a fresh batch + pinned H2D + plan builds + model
-    forward/backward + gradient all-reduce + clip + AdamW; loss read back at the end of the run only."""
+def run_train(args, dev, world, rank, config, hbm_peak):
+    """Secondary metric of BASELINE.json: end-to-end training graphs/sec on configs[0..2] (`pairs` pattern/graph pairs
+    per GPU per step, data parallel).  Every timed step = host collate of a fresh batch + pinned H2D + plan builds +
+    model forward/backward + gradient all-reduce + clip + AdamW; loss read back at the end of the run only."""
     import torch.distributed as dist
 
     from dualmessagepassing_b200 import _lib
     from dualmessagepassing_b200 import train_step as ts
-    cfg = ts.CONFIGS[args.train_config]
-    ds = ts.SyntheticPairDataset(args.train_config, num=4 * cfg["pairs"], seed=2000 + rank)
+    cfg = ts.CONFIGS[config]
+    ds = ts.SyntheticPairDataset(config, num=4 * cfg["pairs"], seed=2000 + rank)
     torch.manual_seed(2000)
     model = ts.SubgraphCountingModel(cfg["hidden"], cfg["labels"][0], cfg["labels"][1]).to(dev)
     opt = torch.optim.AdamW(model.parameters(), lr=1e-3, amsgrad=True)
     rng = np.random.Generator(np.random.PCG64(7 + rank))
     h2d = 0
+    alg = [0, 0]     # sparse-core algorithmic bytes (SURVEY 8d: 4H(9E+4N)+2I per layer fwd+bwd), steps counted
 
     # host collate runs one batch ahead in a worker thread (what a DataLoader worker does for the reference's
     # `GraphAdjDataset.batchify`); H2D + plan builds + the step itself stay on the main thread / current stream
     import queue
     batches = queue.Queue(maxsize=2)
+    stop = threading.Event()
 
     def producer():
-        while True:
+        while not stop.is_set():
             idx = np.sort(rng.choice(ds.num, size=cfg["pairs"], replace=False))
-            batches.put(ts.collate(ds, idx))
+            b = ts.collate(ds, idx)
+            while not stop.is_set():
+                try:
+                    batches.put(b, timeout=0.1)
+                    break
+                except queue.Full:
+                    pass
 
     threading.Thread(target=producer, daemon=True).start()
 
@@ -231,6 +485,10 @@ def run_train(args, dev, world, rank):
         nonlocal h2d
         p, g, y, nb = ts.to_device(batches.get(), dev)
         h2d = nb
+        N = p.number_of_nodes() + g.number_of_nodes()
+        E = p.number_of_edges() + g.number_of_edges()
+        alg[0] += 3 * (4 * cfg["hidden"] * (9 * E + 4 * N) + 2 * (17 * E + 12 * (N + 1)))
+        alg[1] += 1
         return ts.train_step(model, opt, p, g, y, world=world)
 
     for _ in range(5):
@@ -239,6 +497,7 @@ def run_train(args, dev, world, rank):
     if world > 1:
         dist.barrier()
     l0 = _lib.LAUNCHES
+    alg[0] = alg[1] = 0
     t0 = time.perf_counter()
     for _ in range(args.train_steps):
         loss = one_step()
@@ -247,11 +506,15 @@ def run_train(args, dev, world, rank):
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     sec = float(dt.item())
+    stop.set()
+    bytes_per_step = alg[0] / max(alg[1], 1)
     return {"metric": "train graphs/sec (pattern/graph pairs)", "value": cfg["pairs"] * world / sec, "unit": "pairs/s",
             "ms_per_step": sec * 1e3, "steps": args.train_steps, "pairs_per_gpu": cfg["pairs"], "n_gpus": world,
             "scaling": "weak", "config": "BASELINE configs[%d] (%s): 3 shared DMP layers, hidden %d, sum-pool head, "
-            "MSE, AdamW(amsgrad)" % ({"cfg1": 0, "cfg2": 1, "cfg3": 2}[args.train_config], args.train_config, cfg["hidden"]),
+            "MSE, AdamW(amsgrad)" % ({"cfg1": 0, "cfg2": 1, "cfg3": 2}[config], config, cfg["hidden"]),
             "h2d_bytes_per_step": int(h2d), "dmp_launches_per_step": (_lib.LAUNCHES - l0) / args.train_steps,
+            "hbm": {"sparse_core_alg_bytes_per_step": bytes_per_step, "frac": bytes_per_step / sec / 1e9 / hbm_peak,
+                    "note": "whole working set <= 0.4 GB: launch/latency-bound regime (SURVEY 7.2), not a bandwidth claim"},
             "final_loss": float(loss.item())}
 
 
@@ -282,12 +545,13 @@ def run_ours(args):
     peak_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"
 
     # ---- cpu baseline on rank 0, N=1 only, before the GPU run ------------------------------------------
-    cpu_baseline = None
+    cpu_baseline = parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
         sn, se0 = cpu_sample_shape(n, e0, budget_s=10.0)
-        step, sE = cpu_reference_step_fn(sn, se0, h, seed=5000)
+        keep = {}
+        step, sE = cpu_reference_step_fn(sn, se0, h, seed=5000, keep=keep)
         step()
         t0 = time.perf_counter()
         step()
@@ -295,7 +559,13 @@ def run_ours(args):
         cpu_baseline = {"value": sE / dt, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": "1/%d-scale %s: %d nodes, %d edges (incl. reversed), H=%d, 1 warm-up + 1 timed "
                                   "fwd+bwd of oracle/dmp_oracle.py" % (round(E / sE), args.workload, sn, sE, h)}
-        del step
+        # checker leg: our layer on the same sample (production dispatch) against the oracle's result
+        parity = parity_on_sample(keep, h, dev)
+        del keep, step
+        torch.cuda.empty_cache()
+
+    # ---- N > 1: the partitioned path must reproduce the single-GPU layer before it is timed --------------------
+    mg_parity = multi_gpu_parity(rank, world, dev) if world > 1 else None
 
     # ---- build the workload -----------------------------------------------------------------------------
     src, dst, rev = make_graph(n, e0, seed=5000)
@@ -430,11 +700,11 @@ def run_ours(args):
         # DRAM bytes of one full-size launch of that kernel from the committed `ncu --set full` capture (only valid
         # for the workload it was taken on)
         traffic, traffic_src = None, None
-        tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")
+        tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r2_traffic.json")
         if args.workload == "cfg5" and world == 1 and os.path.exists(tpath):
             tk = json.load(open(tpath))["kernels"].get(top.replace("@E", ""))
             if tk is not None and (top.endswith("@E") or not top.startswith("gemm")):
-                traffic, traffic_src = tk["traffic_bytes"], "profiles/r1_traffic.json (%s)" % tk["kernel"]
+                traffic, traffic_src = tk["traffic_bytes"], "profiles/r2_traffic.json (%s)" % tk["kernel"]
         roofline = {"kernel": top, "bound": "hbm", "achieved": kv["gbs"], "peak": hbm_peak, "unit": "GB/s",
                     "frac": kv["frac"], "traffic": traffic, "traffic_source": traffic_src,
                     "alg_bytes_per_launch": kv["alg_bytes"], "avg_launch_ms": kv["avg_ms"], "peak_source": peak_src}
@@ -515,14 +785,24 @@ def run_ours(args):
                        "overlaps the compute of step i), DMPLayer fwd+bwd through the module API, loss scalar + all "
                        "parameter gradients -> host; graph and its plan stay resident"}
 
-    train = None
-    if not args.no_train:
-        if not args.no_e2e:
-            bufs.clear()
-            del prefetch, e2e_step, xv_h, xe_h
-        del xv, xe, gv, ge, graph, runner, plan, step
+    if not args.no_e2e:
+        bufs.clear()
+        del prefetch, e2e_step, xv_h, xe_h
+    del xv, xe, gv, ge, graph, runner, plan, step
+    torch.cuda.empty_cache()
+
+    gpu_baseline = cfg4 = None
+    if world == 1 and not args.no_gpu_baseline:
+        gpu_baseline = run_gpu_baseline(n, e0, h, dev)
+    if world == 1 and not args.no_cfg4:
+        cfg4 = run_cfg4(dev, hbm_peak)
         torch.cuda.empty_cache()
-        train = run_train(args, dev, world, rank)
+
+    train, train_all = None, {}
+    if not args.no_train:
+        for c in (["cfg1", "cfg2", "cfg3"] if args.train_config == "all" else [args.train_config]):
+            train_all[c] = run_train(args, dev, world, rank, c, hbm_peak)
+        train = train_all.get("cfg2") or next(iter(train_all.values()))
 
     if rank == 0:
         line = {
@@ -536,10 +816,13 @@ def run_ours(args):
                        "parallelism": "single GPU" if world == 1 else
                        "dst-range node partition x%d, all-gather fwd / reduce-scatter bwd" % world,
                        "plan_build_ms_excluded": plan_ms,
-                       "dense": "projections on tcgen05 tensor cores, 3xTF32 split with fp32 accumulation "
-                                "(fp32-level accuracy: 1.2e-6 vs fp64; cuBLAS sgemm 5e-7); sparse core in fp32"},
+                       "dense": "projections on tcgen05 tensor cores, 3xTF32 split, cross terms accumulated first "
+                                "(fp32-level accuracy: <= 1e-6 max-norm vs fp64 per product; cuBLAS sgemm 5e-7); sparse "
+                                "core in fp32"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
-            "clocks": clocks, "kernels": kernels, "mlp0": mlp0, "train": train,
+            "clocks": clocks, "parity": parity, "multi_gpu_parity": mg_parity, "gpu_baseline": gpu_baseline,
+            "kernels": kernels, "mlp0": mlp0, "cfg4": cfg4, "train": train,
+            "train_all": {k: v for k, v in train_all.items() if v is not train},
             "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9,
         }
         print(json.dumps(line), flush=True)
@@ -550,9 +833,9 @@ def run_ours(args):
 def main():
     args = parse()
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.impl == "reference":
+    if args.impl in ("reference", "reference_gpu"):
         if int(os.environ.get("RANK", "0")) == 0:
-            run_reference(args)
+            (run_reference if args.impl == "reference" else run_reference_gpu)(args)
         return
     if args.gpus != world and world == 1 and args.gpus > 1:
         # launched without torchrun: re-exec under torch.distributed.run

@@ -43,6 +43,13 @@ def _collectives_worker(rank, world, port, q):
     q_.grad = torch.full((2, 2), 10.0 * (rank + 1))
     par.allreduce_gradients([p, q_], average=True)
     ok = ok and torch.all(p.grad == 1.5) and torch.all(q_.grad == 15.0)
+    # asynchronous forms used by the fused layer (the collective overlaps local work until .wait())
+    g2, w = par.all_gather_rows_async(x)
+    w.wait()
+    ok = ok and torch.equal(g2, g)
+    rs2, w = par.reduce_scatter_rows_async(full)
+    w.wait()
+    ok = ok and torch.equal(rs2, rs)
     a, b = torch.ones(3) * rank, torch.ones(2, 2)
     par.allreduce_tensors_([a, None, b])
     ok = ok and torch.all(a == 1) and torch.all(b == 2)
