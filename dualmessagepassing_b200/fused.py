@@ -58,7 +58,7 @@ _ACT_NAME = {v: k for k, v in _ACT.items()}
 # reduce launch) exceeds what cuBLAS sgemm needs for the whole product
 TC_MIN_ROWS = 16384
 # same-operand projection pairs in ONE launch (dmp_gemm_tf32x3_dual); False = two dmp_gemm_tf32x3 launches (A/B runs)
-DUAL_GEMM = True
+DUAL_GEMM = __import__("os").environ.get("DMP_DUAL_GEMM", "1") != "0"
 
 
 def _dense_ok(t):
