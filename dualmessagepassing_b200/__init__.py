@@ -9,10 +9,10 @@ libdmp_b200.so); there is no CPU fallback.
 from . import constants
 from .act import map_activation_str_to_layer, supported_act_funcs
 from .graph import DMPGraph, add_reversed_edges, batch, build_graph_from_triplets, compute_edgenorm
-from .layers import DMPLayer, DualGraphConv, dual_message_passing
+from .layers import DMPLayer, DMPLRPPoolLayer, DualGraphConv, dual_message_passing
 from .models import DMPNNRepNet, relation_mean_pool
 from .plan import DMPPlan, get_plan
 
-__all__ = ["DMPLayer", "DualGraphConv", "DMPNNRepNet", "DMPGraph", "DMPPlan", "batch", "add_reversed_edges",
+__all__ = ["DMPLayer", "DMPLRPPoolLayer", "DualGraphConv", "DMPNNRepNet", "DMPGraph", "DMPPlan", "batch", "add_reversed_edges",
            "build_graph_from_triplets", "compute_edgenorm", "dual_message_passing", "get_plan",
            "relation_mean_pool", "map_activation_str_to_layer", "supported_act_funcs", "constants"]

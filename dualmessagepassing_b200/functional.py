@@ -416,3 +416,58 @@ def bn_backward(g, x, mean, invstd, gamma, training, out=None):
               _lib.ptr(gamma), _lib.ptr(out), ldo, _lib.ptr(dgamma), _lib.ptr(dbeta), rows, H, int(bool(training)),
               _lib.ptr(ws), ws.numel(), _stream(g), tag="bn_backward", nbytes=5 * 4 * rows * H)
     return out, dgamma, dbeta
+
+
+# ---- sparse matrix x dense rows as a weighted segment reduce (row N4: the perm-pooling of DMPLRPPoolLayer) ----------------
+class SparseRows:
+    """CSR of a torch sparse matrix S and of its transpose, in the layout dmp_segment_reduce takes (int32 indptr, int32
+    column list, fp32 weights in position order).  Built once per matrix (the LRP pooling matrices are preprocessing
+    outputs, fixed per batch) and cached on the tensor."""
+
+    def __init__(self, S):
+        S = S.coalesce() if S.layout == torch.sparse_coo else S.to_sparse_coo().coalesce()
+        _lib.require_cuda(S)
+        rows, cols = S.indices()
+        vals = S.values().float()
+        self.shape = tuple(S.shape)
+
+        def csr(r, c, v, n, width):
+            order = torch.argsort(r * width + c)              # (row, col) order = torch's coalesced storage order
+            r, c, v = r[order], c[order], v[order]
+            indptr = torch.zeros(n + 1, dtype=torch.int32, device=r.device)
+            indptr[1:] = torch.cumsum(torch.bincount(r, minlength=n), 0)
+            return indptr, c.to(torch.int32).contiguous(), v.contiguous()
+
+        self.fwd = csr(rows, cols, vals, self.shape[0], self.shape[1])
+        self.bwd = csr(cols, rows, vals, self.shape[1], self.shape[0])
+
+
+def _sparse_rows(S):
+    cached = getattr(S, "_dmp_rows", None)
+    if cached is None:
+        cached = SparseRows(S)
+        try:
+            S._dmp_rows = cached
+        except AttributeError:
+            pass
+    return cached
+
+
+class _SpMM(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rows, X):
+        indptr, idx, w = rows.fwd
+        ctx.rows = rows
+        return segment_reduce(indptr, idx, X.contiguous(), X.shape[1], w_perm=w, tag="segment_reduce.spmm")
+
+    @staticmethod
+    def backward(ctx, g):
+        indptr, idx, w = ctx.rows.bwd
+        return None, segment_reduce(indptr, idx, g.contiguous(), g.shape[1], w_perm=w, tag="segment_reduce.spmm_bwd")
+
+
+def spmm(S, X):
+    """`torch.sparse.mm(S, X)` (dmplrp.py:180,185) as one deterministic weighted segment reduce: row i of the result is
+    sum_j S[i,j] X[j,:] accumulated sequentially in column order; backward = the same kernel over S^T.  No gradient
+    with respect to S (the reference's pooling matrices are constants)."""
+    return _SpMM.apply(_sparse_rows(S), X.float())

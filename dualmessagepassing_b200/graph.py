@@ -154,24 +154,25 @@ def add_reversed_edges(graph, max_num_edges=None, max_edge_label=None):
 
 
 def compute_edgenorm(graph, norm="in"):
-    """utils.py:437-453."""
-    if "in_deg" not in graph.ndata:
-        graph.ndata["in_deg"] = graph.in_degrees()
-    if "out_deg" not in graph.ndata:
-        graph.ndata["out_deg"] = graph.out_degrees()
-    in_deg = graph.ndata["in_deg"].float()
-    out_deg = graph.ndata["out_deg"].float()
+    """Per-edge normaliser of the UNC pipeline (what `utils.py:437-453` hands to the layers as `edge_norm`): the
+    reciprocal of the destination's in-degree ("in"), of the source's out-degree ("out"), or of the geometric mean of
+    the two ("both"), shape [E,1].  A degree of 0 cannot occur on an existing edge's own endpoint for "in"/"out"; for
+    caller-supplied degree frames that do contain zeros the non-finite entries take the smallest finite value."""
     u, v = graph.all_edges(form="uv", order="eid")
+    deg_in = graph.ndata["in_deg"] if "in_deg" in graph.ndata else graph.ndata.setdefault("in_deg", graph.in_degrees())
+    deg_out = graph.ndata["out_deg"] if "out_deg" in graph.ndata else graph.ndata.setdefault("out_deg", graph.out_degrees())
     if norm == "in":
-        w = in_deg[v].reciprocal().unsqueeze(-1)
+        scale = deg_in[v].float()
     elif norm == "out":
-        w = out_deg[u].reciprocal().unsqueeze(-1)
+        scale = deg_out[u].float()
     elif norm == "both":
-        w = torch.pow(out_deg[u] * in_deg[v], 0.5).reciprocal().unsqueeze(-1)
+        scale = (deg_out[u].float() * deg_in[v].float()).sqrt()
     else:
-        raise ValueError(norm)
-    w.masked_fill_(torch.isnan(w), w.min())
-    w.masked_fill_(torch.isinf(w), w.min())
+        raise ValueError("norm must be 'in', 'out' or 'both', got %r" % (norm,))
+    w = (1.0 / scale).unsqueeze(-1)
+    bad = ~torch.isfinite(w)
+    if bool(bad.any()):
+        w = torch.where(bad, w[~bad].min() if bool((~bad).any()) else torch.zeros((), device=w.device), w)
     return w
 
 

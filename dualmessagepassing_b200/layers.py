@@ -254,6 +254,86 @@ class DMPLayer(nn.Module):
         return self.hidden_dim
 
 
+class DMPLRPPoolLayer(DMPLayer):
+    """SubgraphCountingMatching/models/dmplrp.py:19-198 -- the dual message-passing step of DMPLayer (its body is a
+    verbatim copy in the reference, dmplrp.py:123-168) followed by local relational pooling over permutation
+    sequences (dmplrp.py:180-185):
+
+        z = node_to_perm @ node_out + edge_to_perm @ edge_out          two sparse products  -> [D * L^2, H]
+        y[d, c] = sum_{a, b} z[d, a, b] * lrp_weight[b, c, a] + lrp_bias                     one dense contraction
+        node_out = pooling_matrix @ y                                   one sparse product   -> [N, H]
+
+    The three sparse products run as weighted segment reduces on the sm_100a kernel (`functional.spmm`), sequential in
+    column order like torch's CPU `sparse.mm`.  Same constructor, state_dict (`lrp_weight` [in, hid, L^2], `lrp_bias`)
+    and forward signature / 5-tuple result as the reference."""
+
+    def __init__(self, input_dim, hidden_dim, init_neigenv=4.0, init_eeigenv=4.0, lrp_seq_len=4, bias=True,
+                 num_mlp_layers=2, batch_norm=True, act_func="relu", dropout=0.0):
+        nn.Module.__init__(self)
+        self.input_dim, self.hidden_dim, self.lrp_seq_len = input_dim, hidden_dim, lrp_seq_len
+        self.act_func, self.num_mlp_layers, self.batch_norm, self.num_rels = act_func, num_mlp_layers, batch_norm, 3
+        self.fused = "auto"
+
+        def weight(*extra):
+            return nn.Parameter(torch.empty(input_dim, hidden_dim, *extra))
+
+        # parameter registration and RNG consumption order of dmplrp.py:38-85
+        self.in_weight, self.out_weight = weight(), weight()
+        self.src_weight, self.dst_weight = weight(), weight()
+        self.nloop_weight, self.eloop_weight = weight(), weight()
+        self.lrp_weight = weight(lrp_seq_len * lrp_seq_len)
+        if bias:
+            self.nbias = nn.Parameter(torch.empty(hidden_dim))
+            self.ebias = nn.Parameter(torch.empty(hidden_dim))
+            self.lrp_bias = nn.Parameter(torch.empty(hidden_dim))
+        else:
+            for k in ("nbias", "ebias", "lrp_bias"):
+                self.register_parameter(k, None)
+
+        def mlp():
+            mods = []
+            for i in range(num_mlp_layers):
+                mods.append(nn.Linear(hidden_dim, hidden_dim))
+                if i != num_mlp_layers - 1:
+                    if batch_norm:
+                        mods.append(nn.BatchNorm1d(hidden_dim))
+                    mods.append(map_activation_str_to_layer(act_func))
+            return nn.Sequential(*mods)
+
+        self.nmlp, self.emlp = mlp(), mlp()
+        self.act = map_activation_str_to_layer(act_func)
+        self.drop = nn.Dropout(dropout)
+        for w in (self.in_weight, self.out_weight, self.src_weight, self.dst_weight, self.nloop_weight,
+                  self.eloop_weight):
+            init_weight(w, activation=act_func, init="uniform")
+        init_weight(self.lrp_weight, init="uniform")
+        for m in self.nmlp.modules():
+            init_module(m, activation=act_func, init="uniform")
+        for m in self.emlp.modules():
+            init_module(m, activation=act_func, init="uniform")
+        if bias:
+            for b in (self.nbias, self.ebias, self.lrp_bias):
+                nn.init.zeros_(b)
+        with torch.no_grad():
+            for w in (self.in_weight, self.out_weight, self.nloop_weight):
+                w.div_(init_neigenv)
+            for w in (self.src_weight, self.dst_weight, self.eloop_weight):
+                w.div_(init_eeigenv)
+
+    def forward(self, graph, node_feat, edge_feat, pooling_matrix, node_to_perm_matrix, edge_to_perm_matrix):
+        from .functional import spmm
+        node_out, edge_out = DMPLayer.forward(self, graph, node_feat, edge_feat)
+        z = spmm(node_to_perm_matrix, node_out) + spmm(edge_to_perm_matrix, edge_out)
+        z = z.view(-1, self.lrp_seq_len * self.lrp_seq_len, self.input_dim)
+        y = torch.einsum("dab,bca->dc", z, self.lrp_weight)
+        if self.lrp_bias is not None:
+            y = y + self.lrp_bias
+        return spmm(pooling_matrix, y), edge_out, pooling_matrix, node_to_perm_matrix, edge_to_perm_matrix
+
+    def extra_repr(self):
+        return "in=%s, out=%s\nlrp_seq_len=%s" % (self.input_dim, self.hidden_dim, self.lrp_seq_len)
+
+
 class DualGraphConv(nn.Module):
     """UnsupervisedNodeClassification/Model/DMPNN/src/model.py:117-280 -- same constructor, state_dict
     (including the unused `nfc` / `efc`, model.py:137-138) and forward(graph, node_feat, edge_feat, edge_norm)."""

@@ -110,6 +110,69 @@ def to_device(batch, device, pinned=None):
     return out[0], out[1], y, nbytes
 
 
+class DevicePairDataset:
+    """The flat arrays of a SyntheticPairDataset resident in HBM: batches are then built ON the device
+    (`batch_on_device`, row N1) instead of collating on the host and copying every step."""
+
+    def __init__(self, ds, device):
+        self.device, self.num, self.cfg = torch.device(device), ds.num, ds.cfg
+
+        def put(a, dtype=torch.int64):
+            return torch.from_numpy(np.ascontiguousarray(a)).to(dtype).to(device)
+
+        self.sides = {}
+        for side in ("p", "g"):
+            d = getattr(ds, side)
+            self.sides[side] = dict(noff=put(d["noff"]), eoff=put(d["eoff"]), u=put(d["u"]), v=put(d["v"]),
+                                    vl=put(d["vl"]), el=put(d["el"]), n_host=np.asarray(d["n"], np.int64),
+                                    e_host=np.asarray(d["e"], np.int64))
+        self.counts = put(ds.counts, torch.float32)
+
+
+def batch_on_device(dev_side, sel, sel_host, add_reversed=True):
+    """Disjoint union of graphs `sel` (device int64 [B]; `sel_host` = the same ids on the host, used only to size
+    the outputs) with per-graph reversed-edge blocks, written by two kernels (dmp_batch_offsets + dmp_batch_fill):
+    `dgl.batch` + `add_reversed_edges` semantics (dataset.py:1321-1328, train.py:299-327), bit-identical to the host
+    `_collate_side`.  Returns a DMPGraph with the same frames `to_device` produces."""
+    from . import _lib
+    d = dev_side
+    dev = d["u"].device
+    B = int(len(sel_host))
+    tn = int(d["n_host"][sel_host].sum())
+    te = int(d["e_host"][sel_host].sum()) * (2 if add_reversed else 1)
+    i64 = dict(dtype=torch.int64, device=dev)
+    new_noff, new_eoff = torch.empty(B + 1, **i64), torch.empty(B + 1, **i64)
+    st = _lib.stream_ptr(dev)
+    _lib.call("dmp_batch_offsets", dev, _lib.ptr(sel), B, _lib.ptr(d["noff"]), _lib.ptr(d["eoff"]), int(add_reversed),
+              _lib.ptr(new_noff), _lib.ptr(new_eoff), st, tag="batch_offsets")
+    src, dst = torch.empty(te, **i64), torch.empty(te, **i64)
+    rev = torch.empty(te, dtype=torch.uint8, device=dev)
+    vl, el, ng = torch.empty(tn, **i64), torch.empty(te, **i64), torch.empty(tn, **i64)
+    _lib.call("dmp_batch_fill", dev, _lib.ptr(sel), B, _lib.ptr(d["noff"]), _lib.ptr(d["eoff"]), _lib.ptr(d["u"]),
+              _lib.ptr(d["v"]), _lib.ptr(d["vl"]), _lib.ptr(d["el"]), _lib.ptr(new_noff), _lib.ptr(new_eoff), tn, te,
+              int(add_reversed), _lib.ptr(src), _lib.ptr(dst), _lib.ptr(rev), _lib.ptr(vl), _lib.ptr(el), _lib.ptr(ng),
+              None, st, tag="batch_fill")
+    g = DMPGraph(src, dst, tn)
+    g.edata[REVFLAG] = rev.view(torch.bool)
+    g.ndata[NODELABEL] = vl
+    g.edata[EDGELABEL] = el
+    g.ndata["graph_id"] = ng
+    g._batch_num_nodes = new_noff[1:] - new_noff[:-1]
+    g._batch_num_edges = new_eoff[1:] - new_eoff[:-1]
+    g.rev_layout_hint = "general"   # per-graph [fwd|rev] blocks
+    g.validate_plan = False         # ids are in range by construction: skip the one D2H check per plan
+    return g
+
+
+def collate_on_device(dds, idx):
+    """(pattern, graph, target, h2d bytes) for pairs `idx` (host array): the only host->device traffic is the id list."""
+    sel_host = np.asarray(idx, np.int64)
+    sel = torch.from_numpy(sel_host).pin_memory().to(dds.device, non_blocking=True)
+    p = batch_on_device(dds.sides["p"], sel, sel_host)
+    g = batch_on_device(dds.sides["g"], sel, sel_host)
+    return p, g, dds.counts[sel], sel_host.nbytes
+
+
 class SubgraphCountingModel(nn.Module):
     def __init__(self, hidden, num_vlabels, num_elabels, num_layers=3, act_func="leaky_relu"):
         super().__init__()

@@ -257,6 +257,44 @@ DMP_API int dmp_bn_backward(const float* g, int64_t ldg, const float* x, int64_t
                             float* dbeta, int64_t rows, int64_t H, int training, void* workspace,
                             int64_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Device-side batching (row N1): the disjoint union `GraphAdjDataset.batchify` -> `dgl.batch` builds on the CPU every
+ * step (SCM/dataset.py:1604-1611,1321-1328), over graphs that carry their reversed edges (`add_reversed_edges`,
+ * SCM/train.py:299-327), from a dataset that lives in HBM as flat arrays:
+ *   node_offsets / edge_offsets  int64 [G+1]  graph g owns nodes [no[g], no[g+1]) and ORIGINAL edges [eo[g], eo[g+1])
+ *   u, v                         int64        endpoints LOCAL to the graph;  node_label / edge_label int64 (may be NULL)
+ *   sel                          int64 [B]    the graphs of this batch, in batch order
+ * dmp_batch_offsets writes the exclusive prefix sums of the selected graphs' node counts and (doubled if add_reversed)
+ * edge counts ([B+1] each; DGL: node / edge id offsets of graph i in the batch).  dmp_batch_fill then writes, per batch
+ * graph i: its E0 forward edges (u+off, v+off), then (add_reversed) its E0 reversed edges (v+off, u+off) with rev = 1
+ * -- per-graph edge order preserved, exactly dgl.batch of add_reversed_edges'ed graphs; labels gathered alongside
+ * (the caller applies `label += max_ngel` on reversed edges, train.py:310); node_graph / edge_graph [total] = owning
+ * batch index (may be NULL).  total_nodes / total_edges are host integers (the host keeps the per-graph sizes).
+ */
+DMP_API int dmp_batch_offsets(const int64_t* sel, int64_t num_selected, const int64_t* node_offsets,
+                              const int64_t* edge_offsets, int add_reversed, int64_t* batch_node_offsets,
+                              int64_t* batch_edge_offsets, void* stream);
+DMP_API int dmp_batch_fill(const int64_t* sel, int64_t num_selected, const int64_t* node_offsets,
+                           const int64_t* edge_offsets, const int64_t* u, const int64_t* v, const int64_t* node_label,
+                           const int64_t* edge_label, const int64_t* batch_node_offsets,
+                           const int64_t* batch_edge_offsets, int64_t total_nodes, int64_t total_edges,
+                           int add_reversed, int64_t* src, int64_t* dst, uint8_t* rev, int64_t* node_label_out,
+                           int64_t* edge_label_out, int64_t* node_graph, int64_t* edge_graph, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Ragged <-> padded (row N2): `split_and_batchify_graph_feats(batched_graph_feats, graph_sizes, pre_pad)`
+ * (SCM/utils/dl.py:51-81; called on the rep-net outputs, basemodel.py:1579-1590) without the Python loop over the batch
+ * and without its `.tolist()` synchronisation.  offsets int64 [B+1] = exclusive prefix sums of the graph sizes.
+ *   dmp_ragged_pad     out[b, j, :] = x[offsets[b] + j - start_b, :] inside the graph's window, 0 outside;
+ *                      mask[b, j] = 1 inside (start_b = pre_pad ? max_len - len_b : 0); out is [B*max_len, H]
+ *   dmp_ragged_unpad   the inverse gather (its autograd transpose): out[offsets[b] + k, :] = padded[b, start_b + k, :]
+ */
+DMP_API int dmp_ragged_pad(const float* x, int64_t ldx, const int64_t* offsets, int64_t num_graphs, int64_t max_len,
+                           int64_t H, int pre_pad, float* out, int64_t ld_out, uint8_t* mask, void* stream);
+DMP_API int dmp_ragged_unpad(const float* padded, int64_t ld, const int64_t* offsets, int64_t num_graphs,
+                             int64_t max_len, int64_t H, int pre_pad, float* out, int64_t ld_out, int64_t total_rows,
+                             void* stream);
+
 #ifdef __cplusplus
 }
 #endif

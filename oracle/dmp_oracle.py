@@ -182,6 +182,17 @@ def pattern_rep(layer_params, src, dst, num_nodes, v_emb, e_emb, *, rev=None, ou
     return v, e
 
 
+def lrp_pool(node_out, edge_out, lrp_weight, lrp_bias, pooling_matrix, node_to_perm, edge_to_perm, seq_len):
+    """SubgraphCountingMatching/models/dmplrp.py:180-185 -- local relational pooling after the dual update: three
+    torch.sparse products and one contraction over (sequence position, input feature)."""
+    z = torch.sparse.mm(node_to_perm, node_out) + torch.sparse.mm(edge_to_perm, edge_out)
+    z = z.view(-1, seq_len * seq_len, lrp_weight.shape[0])
+    y = torch.einsum("dab,bca->dc", z, lrp_weight)
+    if lrp_bias is not None:
+        y = y + lrp_bias
+    return torch.sparse.mm(pooling_matrix, y)
+
+
 def relation_mean_pool(z, rel, num_rels):
     """model.py:319-325 -- per-relation masked mean of edge states."""
     rows = []

@@ -121,3 +121,37 @@ def erdos_renyi(rng, n, e0, self_loops=False):
         v = rng.integers(0, n - 1, size=e0, dtype=np.int64)
         v = v + (v >= u)
     return u, v
+
+
+def split_and_batchify(feats, sizes, pre_pad=False):
+    """SubgraphCountingMatching/utils/dl.py:51-81 restated with the reference's own loop: ragged [sum(sizes), H] ->
+    (padded [B, max, H], mask [B, max])."""
+    feats = np.asarray(feats)
+    sizes = [int(x) for x in np.asarray(sizes).reshape(-1)]
+    bsz, mx = len(sizes), max(sizes)
+    out = np.zeros((bsz, mx) + feats.shape[1:], feats.dtype)
+    mask = np.zeros((bsz, mx), bool)
+    idx = 0
+    for i, l in enumerate(sizes):
+        if pre_pad:
+            out[i, mx - l:] = feats[idx:idx + l]
+            mask[i, mx - l:] = True
+        else:
+            out[i, :l] = feats[idx:idx + l]
+            mask[i, :l] = True
+        idx += l
+    return out, mask
+
+
+def len_to_mask(lens, max_len=-1, pre_pad=False):
+    """dl.py:113-127 restated (loop over the batch)."""
+    lens = [int(x) for x in lens]
+    if max_len == -1:
+        max_len = max(lens)
+    mask = np.ones((len(lens), max_len), bool)
+    for i, l in enumerate(lens):
+        if pre_pad:
+            mask[i, :max_len - l] = False
+        else:
+            mask[i, l:] = False
+    return mask

@@ -204,9 +204,55 @@ def run_unc():
              **st, **grads(layer))
 
 
+def run_dmplrp():
+    """DMPLRPPoolLayer (SubgraphCountingMatching/models/dmplrp.py:19-198, unmodified): the dual message-passing step +
+    local relational pooling through three torch.sparse products and one einsum.  The pooling matrices are random
+    sparse matrices of the shapes the LRP preprocessing produces ([D*L^2, N], [D*L^2, E], [N, D])."""
+    _dgl_shim.install()
+    sys.path.insert(0, os.path.join(REF, "SubgraphCountingMatching"))
+    from models.dmplrp import DMPLRPPoolLayer  # the reference class, unmodified
+    import constants as C
+    for ci, (name, n, e0, h, L, D, mlp, bn, act) in enumerate([
+            ("lrp_h16_mlp2", 30, 50, 16, 4, 22, 2, False, "leaky_relu"),
+            ("lrp_h12_mlp0_bn", 18, 40, 12, 3, 15, 0, True, "tanh")]):
+        rng = np.random.Generator(np.random.PCG64(7300 + ci))
+        torch.manual_seed(7300 + ci)
+        u, v = er_graph(rng, n, e0, False)
+        g = _dgl_shim.ShimGraph(u, v, n)
+        uu, vv = g.all_edges(form="uv", order="eid")
+        g.add_edges(vv, uu, data={C.REVFLAG: torch.ones((len(u),), dtype=torch.bool)})
+        E = g.number_of_edges()
+        layer = DMPLRPPoolLayer(h, h, lrp_seq_len=L, num_mlp_layers=mlp, batch_norm=bn, act_func=act)
+        layer.train()
+
+        def sparse(rows, cols, nnz):
+            idx = np.unique(np.stack([rng.integers(0, rows, nnz), rng.integers(0, cols, nnz)]), axis=1)
+            val = torch.from_numpy(rng.standard_normal(idx.shape[1]).astype(np.float32))
+            return torch.sparse_coo_tensor(torch.from_numpy(idx), val, (rows, cols)).coalesce()
+
+        n2p, e2p, pool = sparse(D * L * L, n, 3 * D * L), sparse(D * L * L, E, 3 * D * L), sparse(n, D, 4 * n)
+        xv = torch.randn(n, h, requires_grad=True)
+        xe = torch.randn(E, h, requires_grad=True)
+        gv, ge = torch.randn(n, h), torch.randn(E, h)
+        st = state(layer)
+        nv, ne, *_ = layer(g, xv, xe, pool, n2p, e2p)
+        ((nv * gv).sum() + (ne * ge).sum()).backward()
+        src, dst = g.all_edges()
+        mats = {}
+        for k, m in (("n2p", n2p), ("e2p", e2p), ("pool", pool)):
+            mats[k + "_idx"], mats[k + "_val"], mats[k + "_shape"] = m.indices(), m.values(), np.asarray(m.shape)
+        save(name, src=src, dst=dst, num_nodes=n, rev=g.edata[C.REVFLAG], out_deg=g.ndata[C.OUTDEGREE],
+             node_feat=xv, edge_feat=xe, grad_node_out=gv, grad_edge_out=ge, node_out=nv, edge_out=ne,
+             grad_node_feat=xv.grad, grad_edge_feat=xe.grad, meta=np.asarray([h, L, D, mlp, int(bn)]),
+             act=np.asarray(act), **mats, **st, **grads(layer))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "unc":
         run_unc()
+    elif len(sys.argv) > 1 and sys.argv[1] == "lrp":
+        run_dmplrp()
     else:
         run_scm()
+        run_dmplrp()
         subprocess.check_call([sys.executable, os.path.abspath(__file__), "unc"])

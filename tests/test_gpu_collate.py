@@ -1,0 +1,103 @@
+"""Rows N1 / N2: device-side batching (dmp_batch_offsets / dmp_batch_fill) bit-exact against the host collate (itself
+checked against the graph oracle in test_train_step.py), and the ragged <-> padded kernels against the restated
+reference loop (oracle/graph_oracle.py: dl.py:51-81,113-127)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import graph_oracle as go
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg,num,bsz", [("cfg1", 200, 64), ("cfg2", 700, 512), ("cfg3", 100, 64), ("cfg1", 2600, 2500)])
+def test_device_batch_equals_host_collate(cfg, num, bsz):
+    from dualmessagepassing_b200 import train_step as ts
+    from dualmessagepassing_b200.constants import EDGELABEL, NODELABEL, REVFLAG
+    ds = ts.SyntheticPairDataset(cfg, num=num, seed=11)
+    dds = ts.DevicePairDataset(ds, "cuda")
+    rng = np.random.Generator(np.random.PCG64(5))
+    idx = np.sort(rng.choice(num, size=bsz, replace=False))
+    host = ts.collate(ds, idx)
+    p, g, y, nbytes = ts.collate_on_device(dds, idx)
+    assert nbytes == idx.nbytes
+    for side, dg in (("p", p), ("g", g)):
+        want = host[side]
+        src, dst = dg.all_edges()
+        assert np.array_equal(src.cpu().numpy(), want["src"]) and np.array_equal(dst.cpu().numpy(), want["dst"])
+        assert np.array_equal(dg.edata[REVFLAG].cpu().numpy(), want["rev"])
+        assert np.array_equal(dg.ndata[NODELABEL].cpu().numpy(), want["vl"])
+        assert np.array_equal(dg.edata[EDGELABEL].cpu().numpy(), want["el"])
+        assert np.array_equal(dg.ndata["graph_id"].cpu().numpy(), want["node_graph"])
+        assert np.array_equal(dg.batch_num_nodes().cpu().numpy(), want["n"])
+        assert np.array_equal(dg.batch_num_edges().cpu().numpy(), want["e"])
+        assert dg.number_of_nodes() == want["num_nodes"]
+    assert np.array_equal(y.cpu().numpy(), host["y"])
+    # without reversed edges: plain dgl.batch
+    sel = torch.from_numpy(idx).cuda()
+    g0 = ts.batch_on_device(dds.sides["g"], sel, idx, add_reversed=False)
+    graphs = [(ds.g["u"][ds.g["eoff"][i]:ds.g["eoff"][i + 1]], ds.g["v"][ds.g["eoff"][i]:ds.g["eoff"][i + 1]],
+               int(ds.g["n"][i])) for i in idx]
+    s0, d0, n0, bn, be = go.batch_graphs(graphs)
+    src, dst = g0.all_edges()
+    assert np.array_equal(src.cpu().numpy(), s0) and np.array_equal(dst.cpu().numpy(), d0) and g0.number_of_nodes() == n0
+    assert not bool(g0.edata[REVFLAG].any())
+
+
+@pytest.mark.gpu
+def test_train_step_on_device_batches_matches_host_batches():
+    """Same model, same pairs: the loss from device-built batches equals the loss from host-collated ones bit for bit."""
+    from dualmessagepassing_b200 import train_step as ts
+    ds = ts.SyntheticPairDataset("cfg1", num=64, seed=3)
+    dds = ts.DevicePairDataset(ds, "cuda")
+    torch.manual_seed(0)
+    model = ts.SubgraphCountingModel(64, 1, 1).cuda()
+    idx = np.arange(0, 64, 2)
+    p, g, y, _ = ts.to_device(ts.collate(ds, idx), torch.device("cuda"))
+    p2, g2, y2, _ = ts.collate_on_device(dds, idx)
+    a = model(p, g, union=ts.union_graph(p, g))
+    b = model(p2, g2, union=ts.union_graph(p2, g2))
+    assert torch.equal(a, b) and torch.equal(y, y2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pre_pad", [False, True])
+@pytest.mark.parametrize("H", [1, 50, 128])
+def test_ragged_pad_matches_reference_loop(pre_pad, H):
+    from dualmessagepassing_b200 import ragged
+    rng = np.random.Generator(np.random.PCG64(H))
+    sizes = rng.integers(1, 40, size=97)
+    x = rng.standard_normal((int(sizes.sum()), H)).astype(np.float32)
+    want, wmask = go.split_and_batchify(x, sizes, pre_pad)
+    xt = torch.from_numpy(x).cuda().requires_grad_(True)
+    got, mask = ragged.split_and_batchify_graph_feats(xt, torch.from_numpy(sizes).cuda(), pre_pad=pre_pad)
+    assert np.array_equal(got.detach().cpu().numpy(), want) and np.array_equal(mask.cpu().numpy(), wmask)
+    # caller-supplied max_size (no synchronisation) larger than the largest graph
+    got2, mask2 = ragged.split_and_batchify_graph_feats(xt, torch.from_numpy(sizes).cuda(), pre_pad=pre_pad, max_size=48)
+    assert got2.shape == (97, 48, H) and int(mask2.sum()) == int(sizes.sum())
+    sl = slice(48 - want.shape[1], None) if pre_pad else slice(0, want.shape[1])
+    assert np.array_equal(got2[:, sl].detach().cpu().numpy(), want)
+    # backward = the inverse gather
+    w = torch.randn_like(got)
+    (got * w).sum().backward()
+    rows = []
+    for i, l in enumerate(sizes):
+        st = want.shape[1] - l if pre_pad else 0
+        rows.append(w[i, st:st + l])
+    assert torch.equal(xt.grad, torch.cat(rows))
+    # equal sizes: the reference's .view fast path
+    eq, m = ragged.split_and_batchify_graph_feats(xt[:90].detach(), torch.full((9,), 10).cuda())
+    assert torch.equal(eq, xt[:90].detach().view(9, 10, H)) and bool(m.all())
+
+
+def test_len_to_mask_and_deferred_scalars_cpu():
+    from dualmessagepassing_b200 import ragged
+    lens = [3, 1, 4, 4, 2]
+    for pre in (False, True):
+        for mx in (-1, 6):
+            got = ragged.batch_convert_len_to_mask(torch.tensor(lens), mx, pre)
+            assert np.array_equal(got.numpy(), go.len_to_mask(lens, mx, pre))
+    d = ragged.DeferredScalars()
+    for i in range(3):
+        d.add(loss=torch.tensor(float(i)), reg=torch.tensor(2.0 * i))
+    out = d.fetch()
+    assert out == {"loss": [0.0, 1.0, 2.0], "reg": [0.0, 2.0, 4.0]} and d.fetch() == {}

@@ -104,6 +104,38 @@ def test_dualgraphconv_matches_reference_golden(name):
                                    atol=2e-5 * max(1.0, float(case["grads"][k].abs().max())), msg=lambda m: k + m)
 
 
+@pytest.mark.parametrize("name", _golden.case_names("lrp_"))
+def test_dmplrp_pool_layer_matches_reference_golden(name):
+    """Row N4: DMPLRPPoolLayer = the dual update + perm-pooling as three weighted segment reduces (functional.spmm)."""
+    case = _golden.load(name)
+    h, L, D, mlp, bn = [int(x) for x in case["meta"]]
+    layer = dmp.DMPLRPPoolLayer(h, h, lrp_seq_len=L, num_mlp_layers=mlp, batch_norm=bool(bn), act_func=case["act"])
+    layer.load_state_dict(case["params"])
+    layer.cuda().train()
+    g = _graph_from_case(case, "scm")
+    mats = {k: torch.sparse_coo_tensor(case[k + "_idx"], case[k + "_val"],
+                                       tuple(int(x) for x in case[k + "_shape"])).coalesce().cuda()
+            for k in ("n2p", "e2p", "pool")}
+    xv = case["node_feat"].cuda().requires_grad_(True)
+    xe = case["edge_feat"].cuda().requires_grad_(True)
+    nv, ne, p_, n_, e_ = layer(g, xv, xe, mats["pool"], mats["n2p"], mats["e2p"])
+    assert p_ is mats["pool"] and n_ is mats["n2p"] and e_ is mats["e2p"]      # dmplrp.py:187 returns them unchanged
+    close(nv, case["node_out"], "node_out")
+    close(ne, case["edge_out"], "edge_out")
+    ((nv * case["grad_node_out"].cuda()).sum() + (ne * case["grad_edge_out"].cuda()).sum()).backward()
+    close(xv.grad, case["grad_node_feat"], "grad_node_feat")
+    close(xe.grad, case["grad_edge_feat"], "grad_edge_feat")
+    for k, p in layer.named_parameters():
+        got = p.grad if p.grad is not None else torch.zeros_like(p)
+        torch.testing.assert_close(got.cpu(), case["grads"][k], rtol=1e-5,
+                                   atol=2e-5 * max(1.0, float(case["grads"][k].abs().max())), msg=lambda m: k + m)
+    # the sparse products alone against torch's CPU sparse.mm (same column order; torch may contract w*x + acc into an
+    # FMA, the kernel rounds the product separately: 1-ulp differences)
+    from dualmessagepassing_b200.functional import spmm
+    x = torch.randn(mats["n2p"].shape[1], h)
+    torch.testing.assert_close(spmm(mats["n2p"], x.cuda()).cpu(), torch.sparse.mm(mats["n2p"].cpu(), x), rtol=1e-6, atol=1e-6)
+
+
 @pytest.mark.parametrize("side", ["graph", "pattern"])
 def test_rep_loop_matches_reference_golden(side):
     case = _golden.load("scm_%s_rep_3layers" % side)

@@ -36,6 +36,18 @@ def test_dualgraphconv_init_is_seed_identical_to_reference(name):
         assert torch.equal(v, case["params"][k]), k
 
 
+@pytest.mark.parametrize("name,seed", [("lrp_h16_mlp2", 7300), ("lrp_h12_mlp0_bn", 7301)])
+def test_dmplrp_init_is_seed_identical_to_reference(name, seed):
+    case = _golden.load(name)
+    h, L, D, mlp, bn = [int(x) for x in case["meta"]]
+    torch.manual_seed(seed)
+    layer = dmp.DMPLRPPoolLayer(h, h, lrp_seq_len=L, num_mlp_layers=mlp, batch_norm=bool(bn), act_func=case["act"])
+    sd = layer.state_dict()
+    assert set(sd) == set(case["params"])      # lrp_weight [in, hid, L*L], lrp_bias (dmplrp.py:45-53)
+    for k, v in sd.items():
+        assert torch.equal(v, case["params"][k]), k
+
+
 def test_state_dict_roundtrip_and_registered_none_bias():
     layer = dmp.DMPLayer(8, 12, bias=False, num_mlp_layers=2, batch_norm=True, act_func="relu")
     assert layer.nbias is None and layer.ebias is None

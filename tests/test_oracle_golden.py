@@ -95,3 +95,25 @@ def test_rep_loop_matches_reference(side):
     for i, g in enumerate(_golden.split_layers(case["grads"])):
         for k, v in g.items():
             torch.testing.assert_close(layers[i][k].grad, v, rtol=1e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("name", _golden.case_names("lrp_"))
+def test_dmplrp_pool_layer_matches_reference(name):
+    """dmplrp.py:19-198: the oracle's DMPLayer body + lrp_pool reproduce the reference class bit for bit."""
+    case = _golden.load(name)
+    h, L, D, mlp, bn = [int(x) for x in case["meta"]]
+    P = _float_params(case["params"])
+    xv = case["node_feat"].clone().requires_grad_(True)
+    xe = case["edge_feat"].clone().requires_grad_(True)
+    mats = {k: torch.sparse_coo_tensor(case[k + "_idx"], case[k + "_val"], tuple(int(x) for x in case[k + "_shape"])).coalesce()
+            for k in ("n2p", "e2p", "pool")}
+    nv, ne = dmp_oracle.dmp_layer(P, case["src"], case["dst"], case["num_nodes"], xv, xe, rev=case["rev"],
+                                  out_deg=case["out_deg"], flavour="scm", act_func=case["act"])
+    out = dmp_oracle.lrp_pool(nv, ne, P["lrp_weight"], P.get("lrp_bias"), mats["pool"], mats["n2p"], mats["e2p"], L)
+    assert torch.equal(out, case["node_out"]) and torch.equal(ne, case["edge_out"])
+    ((out * case["grad_node_out"]).sum() + (ne * case["grad_edge_out"]).sum()).backward()
+    torch.testing.assert_close(xv.grad, case["grad_node_feat"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(xe.grad, case["grad_edge_feat"], rtol=1e-5, atol=1e-6)
+    for k, g in case["grads"].items():
+        got = P[k].grad if P[k].grad is not None else torch.zeros_like(P[k])
+        torch.testing.assert_close(got, g, rtol=1e-5, atol=2e-6, msg=lambda m: k + ": " + m)
