@@ -41,6 +41,36 @@ def segment_reduce(indptr, eid, V, H, *, w_perm=None, rev_col_offset=0, base=Non
     return out
 
 
+def segment_reduce_two_level(indptr, eid, V, H, *, chunk=1024, w_perm=None, rev_col_offset=0, base=None, bias=None, mode=0,
+                             out=None, tag=None):
+    """Same reduction for graphs with very long segments (hubs: Yelp has 30.5 M links on 82 k nodes): every segment is
+    cut into chunks of `chunk` positions, the chunks are reduced in parallel (sequentially inside a chunk, ascending
+    position) and the chunk partials of a segment are then added in ascending chunk order.  Deterministic and run-to-run
+    bit-stable, but NOT the strictly sequential order of `segment_reduce` for segments longer than `chunk` (fp32 addition
+    is not associative): use it where the reference's own order is not sequential either (pooling by `sum(dim=0)`,
+    model.py:319-325) or as an explicit throughput option; shorter segments are bit-identical.  No host synchronisation:
+    the chunk table is sized by its upper bound nseg + E/chunk."""
+    nseg = indptr.numel() - 1
+    E = eid.numel()
+    t_max = nseg + E // chunk + 1
+    ip = indptr.to(torch.int64)
+    nch = (ip[1:] - ip[:-1] + (chunk - 1)) // chunk                       # chunks per segment (0 for empty segments)
+    ch_off = torch.zeros(nseg + 1, dtype=torch.int64, device=indptr.device)
+    ch_off[1:] = torch.cumsum(nch, 0)
+    t = torch.arange(t_max + 1, device=indptr.device)
+    owner = torch.searchsorted(ch_off, t, right=True) - 1                  # segment of chunk t (nseg for the padding)
+    inside = owner < nseg
+    own = owner.clamp(max=max(nseg - 1, 0))
+    start = ip[own] + (t - ch_off[own]) * chunk
+    fine = torch.where(inside, start, torch.full_like(start, E)).to(torch.int32)   # [t_max + 1]: refined indptr
+    split = bool(mode & _lib.SEG_SPLIT_BY_REV)
+    partial = segment_reduce(fine, eid, V, H, w_perm=w_perm, rev_col_offset=rev_col_offset, mode=mode & ~_lib.SEG_NEGATE_OUT,
+                             tag=(tag or "segment_reduce") + ".chunks")
+    ident = torch.arange(t_max, dtype=torch.int32, device=indptr.device)
+    return segment_reduce(ch_off.to(torch.int32), ident, partial, 2 * H if split else H, base=base, bias=bias,
+                          mode=mode & _lib.SEG_NEGATE_OUT, out=out, tag=(tag or "segment_reduce") + ".combine")
+
+
 def edge_update(plan, S, P, Qd, Qs, ebias, order, out=None, edge_agg=None):
     """Raw call of dmp_edge_update; `out` may be S itself (in place)."""
     if S.shape[0] != plan.E or (P is not None and P.shape[0] != plan.E):

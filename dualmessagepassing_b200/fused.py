@@ -17,7 +17,15 @@ import torch
 
 from . import _lib
 from .functional import (bn_act, bn_backward, bn_stats, edge_backward, edge_update, gemm_tf32x3, gemm_tf32x3_dual,
-                         gemm_tn_tf32x3, segment_reduce)
+                         gemm_tn_tf32x3, segment_reduce_two_level)
+from .functional import segment_reduce as _segment_reduce_seq
+
+
+def segment_reduce(indptr, eid, V, H, *, plan=None, **kw):
+    """Sequential-order reduce (DGL's fn.sum order, bit for bit) unless the plan asks for chunked long segments."""
+    if plan is not None and plan.long_chunk:
+        return segment_reduce_two_level(indptr, eid, V, H, chunk=int(plan.long_chunk), **kw)
+    return _segment_reduce_seq(indptr, eid, V, H, **kw)
 
 _ACT = {"none": _lib.ACT_NONE, "relu": _lib.ACT_RELU, "leaky_relu": _lib.ACT_LEAKY_RELU,
         "tanh": _lib.ACT_TANH, "sigmoid": _lib.ACT_SIGMOID}
@@ -286,7 +294,7 @@ class _FusedDMPLayer(torch.autograd.Function):
         m_off = 0 if plan.rev_layout in ("none", "halves") else H   # column offset of the reversed branch in [E, 2H]
         if agg_first:
             split = plan.rev is not None
-            A2 = segment_reduce(csc_indptr, plan.csc_eid, X_e, Din, w_perm=norm_perm,
+            A2 = segment_reduce(csc_indptr, plan.csc_eid, X_e, Din, plan=plan, w_perm=norm_perm,
                                 mode=_lib.SEG_SIGN_BY_REV | (_lib.SEG_SPLIT_BY_REV if split else 0),
                                 tag="segment_reduce.node_fwd")
             node_pre = _rowmm(X_v, nloop_w.t(), bias=nbias)
@@ -396,8 +404,8 @@ class _FusedDMPLayer(torch.autograd.Function):
             X_v_full = ctx.X_v_full
 
         # ---- sparse core backward: two sorted-segment sums of gE, one gather of gN ------
-        dQd = segment_reduce(plan.a_indptr, plan.a_eid, gE, H, tag="segment_reduce.dQd_bwd")
-        dQs = segment_reduce(plan.b_indptr, plan.b_eid, gE, H, mode=_lib.SEG_NEGATE_OUT,
+        dQd = segment_reduce(plan.a_indptr, plan.a_eid, gE, H, plan=plan, tag="segment_reduce.dQd_bwd")
+        dQs = segment_reduce(plan.b_indptr, plan.b_eid, gE, H, plan=plan, mode=_lib.SEG_NEGATE_OUT,
                              tag="segment_reduce.dQs_bwd")
         w_sd = src_w - dst_w
         Din = in_w.shape[0]

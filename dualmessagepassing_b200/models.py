@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .functional import gate_residual, segment_reduce
+from .functional import gate_residual, segment_reduce_two_level
 from .layers import DMPLayer
 
 
@@ -80,7 +80,10 @@ class _RelationPool(torch.autograd.Function):
         counts = torch.bincount(rel, minlength=num_rels)
         indptr = torch.zeros(num_rels + 1, dtype=torch.int32, device=z.device)
         indptr[1:] = torch.cumsum(counts, 0)
-        sums = segment_reduce(indptr, order.to(torch.int32), z, z.shape[1])
+        # num_rels segments of ~E/num_rels rows each: chunked so that the whole GPU works on them (the reference's
+        # `masked_fill(...).sum(dim=0)` has no sequential order to preserve)
+        sums = segment_reduce_two_level(indptr, order.to(torch.int32), z, z.shape[1], chunk=512,
+                                        tag="segment_reduce.rel_pool")
         denom = counts.to(z.dtype) + 1e-8
         ctx.save_for_backward(rel, denom)
         return sums / denom.unsqueeze(-1)

@@ -100,6 +100,10 @@ class DMPPlan:
                 self.rev_split = st[1] - 1
         self._norm_perm = {}
         self._mirrored = None
+        # graphs with hub nodes (power-law degree): set `graph.long_segment_chunk = 1024` (or this attribute) and the
+        # layer's three segment reductions cut segments longer than that into parallel chunks
+        # (functional.segment_reduce_two_level: deterministic, but not DGL's strictly sequential order on those hubs)
+        self.long_chunk = None
         del ws
 
     @property
@@ -165,6 +169,8 @@ def get_plan(graph, rev_key, deg_key, validate=True):
         hint = getattr(graph, "rev_layout_hint", None)
         validate = getattr(graph, "validate_plan", validate)
         plan = DMPPlan(src, dst, n, rev=rev, out_deg=deg, validate=validate, rev_layout=hint)
+        plan.long_chunk = getattr(graph, "long_segment_chunk", None)
+        plan._key_refs = (src, dst, rev, deg)   # keep the key tensors alive: a recycled address must not hit this plan
         cache.clear()
         cache[key] = plan
         if deg is None:

@@ -1,13 +1,9 @@
-#!/bin/bash
-# ncu evidence for profiles/: (1) launch list of the bench command, (2) --set full of one full-size launch of every
-# hand-written hot kernel.  Single GPU only.  Outputs under gpurun_out/; summarise here with scripts/summarise_ncu.py.
-set -x
+# usage: scripts/ncu_capture.sh <tag>   (on the GPU box; ~5 min)
+#  1. launch list of the bench command (per-launch gpu__time_duration, cold cache, serialised: compare SHARES)
+#  2. --set full of one full-size launch of every hot kernel (scripts/ncu_kernels_fullsize.py)
 mkdir -p gpurun_out
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
-  --log-file gpurun_out/launches_cfg5_r1_final2.csv \
-  python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-train --no-mlp0 > gpurun_out/ncu_list_final2.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on \
-  -k regex:"segment_reduce_kernel|edge_update|edge_backward_kernel|tf32x3_gemm_kernel|tf32x3_gemm_tn_kernel" \
-  -f -o gpurun_out/prof_final2_r1 python scripts/ncu_kernels_fullsize.py > gpurun_out/ncu_full_final2.log 2>&1
-tail -3 gpurun_out/ncu_full_final2.log
-ls -la gpurun_out/prof_final2_r1.ncu-rep
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_$1.csv \
+  python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-train --no-mlp0 --no-cfg4 --no-gpu-baseline \
+  > gpurun_out/ncu_list_$1.log 2>&1
+tail -1 gpurun_out/ncu_list_$1.log | head -c 300
+bash scripts/ncu_full_only.sh $1

@@ -146,6 +146,44 @@ def test_long_segment_hub_bit_exact_and_deterministic():
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])  # run-to-run bit stability
 
 
+def test_million_edge_hub_sequential_bit_exact_and_two_level_close():
+    """A 1 M-edge segment: the default path stays the strictly sequential sum (bit-exact vs the C oracle); the chunked
+    two-level option is deterministic, bit-identical on segments no longer than a chunk, and within fp32 reassociation
+    error of an fp64 sum on the hub."""
+    from dualmessagepassing_b200 import _lib, functional as F
+    s, d, r = hub_graph(22, 3000, 20000, 1_000_000)
+    plan = _plan(s, d, 3000, r)
+    cp = _cpu_plan(plan)
+    E, H = len(s), 64
+    M = torch.randn(E, H, generator=torch.Generator().manual_seed(4))
+    want = sc.seg_reduce(cp["csc_indptr"], cp["csc_eid"], M, H, mode=_lib.SEG_SIGN_BY_REV)
+    Mg = M.cuda()
+    got = F.segment_reduce(plan.csc_indptr, plan.csc_eid, Mg, H, mode=_lib.SEG_SIGN_BY_REV)
+    assert torch.equal(got.cpu(), want)
+    for mode in (_lib.SEG_SIGN_BY_REV, _lib.SEG_SIGN_BY_REV | _lib.SEG_SPLIT_BY_REV, _lib.SEG_NEGATE_OUT):
+        seq = F.segment_reduce(plan.csc_indptr, plan.csc_eid, Mg, H, mode=mode)
+        two = [F.segment_reduce_two_level(plan.csc_indptr, plan.csc_eid, Mg, H, chunk=1024, mode=mode) for _ in range(2)]
+        assert torch.equal(two[0], two[1])
+        lens = (plan.csc_indptr[1:] - plan.csc_indptr[:-1]).long()
+        short = lens <= 1024
+        assert torch.equal(two[0][short], seq[short])              # one chunk per segment: the same sequence of adds
+        # hub rows: compare both orders with an fp64 sum of the same terms
+        hub = int(torch.argmax(lens))
+        lo, hi = int(plan.csc_indptr[hub]), int(plan.csc_indptr[hub + 1])
+        e = plan.csc_eid[lo:hi].long()
+        rows, rv = (e & 0x7FFFFFFF), (e >> 31) & 1
+        x = Mg[rows].double()
+        if mode & _lib.SEG_SIGN_BY_REV:
+            x = torch.where(rv.bool().unsqueeze(1), x, -x)
+        if mode & _lib.SEG_SPLIT_BY_REV:
+            ref = torch.cat([(x * (rv == 0).unsqueeze(1)).sum(0), (x * (rv == 1).unsqueeze(1)).sum(0)])
+        else:
+            ref = x.sum(0) * (-1 if mode & _lib.SEG_NEGATE_OUT else 1)
+        scale = float(x.abs().sum(0).max())
+        assert float((two[0][hub].double() - ref).abs().max()) <= 2e-7 * scale
+        assert float((seq[hub].double() - ref).abs().max()) <= 2e-6 * scale   # 1 M sequential fp32 adds drift further
+
+
 def test_strided_operands_use_leading_dimension():
     from dualmessagepassing_b200 import _lib, functional as F
     s, d, r = make_graph(seed=5, n=40, e0=200, rev="halves")
