@@ -50,8 +50,8 @@ SIGNATURES = {
     "dmp_gemm_tf32x3": [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _i32, _f32, _vp],
     "dmp_gemm_tf32x3_dual": [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _i32, _vp],
     "dmp_batch_offsets": [_vp, _i64, _vp, _vp, _i32, _vp, _vp, _vp],
-    "dmp_batch_fill": [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
-                       _vp, _vp],
+    "dmp_batch_fill": [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp,
+                       _vp, _vp, _vp],
     "dmp_ragged_pad": [_vp, _i64, _vp, _i64, _i64, _i64, _i32, _vp, _i64, _vp, _vp],
     "dmp_ragged_unpad": [_vp, _i64, _vp, _i64, _i64, _i64, _i32, _vp, _i64, _i64, _vp],
     "dmp_bn_workspace_bytes": [_i64, ctypes.POINTER(ctypes.c_int64)],

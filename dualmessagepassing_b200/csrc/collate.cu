@@ -60,6 +60,7 @@ struct BatchFillParams {
   const int64_t* new_noff; const int64_t* new_eoff;
   int64_t total_nodes, total_edges;
   int reversed;
+  int padded;     // total_* are PADDED sizes; the real totals are new_noff[B] / new_eoff[B] (device): rows past them are dummies
   int64_t* src; int64_t* dst; uint8_t* rev; int64_t* vlabel_out; int64_t* elabel_out; int64_t* node_graph;
   int64_t* edge_graph;
 };
@@ -67,8 +68,15 @@ struct BatchFillParams {
 __global__ void __launch_bounds__(kThreads) batch_fill_kernel(const BatchFillParams p) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t total = p.total_nodes + p.total_edges;
+  const int64_t real_nodes = p.padded ? __ldg(p.new_noff + p.B) : p.total_nodes;
+  const int64_t real_edges = p.padded ? __ldg(p.new_eoff + p.B) : p.total_edges;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
     if (t < p.total_nodes) {
+      if (t >= real_nodes) {          // padding: isolated dummy node of a dummy graph B (dropped by every pooling)
+        if (p.vlabel_out) p.vlabel_out[t] = 0;
+        if (p.node_graph) p.node_graph[t] = p.B;
+        continue;
+      }
       const int64_t i = owner_of(p.new_noff, p.B, t);
       const int64_t g = __ldg(p.sel + i);
       const int64_t from = __ldg(p.noff + g) + (t - __ldg(p.new_noff + i));
@@ -76,6 +84,14 @@ __global__ void __launch_bounds__(kThreads) batch_fill_kernel(const BatchFillPar
       if (p.node_graph) p.node_graph[t] = i;
     } else {
       const int64_t k = t - p.total_nodes;
+      if (k >= real_edges) {          // padding: a forward self-loop on the LAST (dummy) node -- touches no real row
+        p.src[k] = p.total_nodes - 1;
+        p.dst[k] = p.total_nodes - 1;
+        if (p.rev) p.rev[k] = 0;
+        if (p.elabel_out) p.elabel_out[k] = 0;
+        if (p.edge_graph) p.edge_graph[k] = p.B;
+        continue;
+      }
       const int64_t i = owner_of(p.new_eoff, p.B, k);
       const int64_t g = __ldg(p.sel + i);
       const int64_t e0 = __ldg(p.eoff + g + 1) - __ldg(p.eoff + g);
@@ -183,8 +199,9 @@ extern "C" int dmp_batch_fill(const int64_t* sel, int64_t num_selected, const in
                               const int64_t* edge_offsets, const int64_t* u, const int64_t* v, const int64_t* node_label,
                               const int64_t* edge_label, const int64_t* batch_node_offsets,
                               const int64_t* batch_edge_offsets, int64_t total_nodes, int64_t total_edges,
-                              int add_reversed, int64_t* src, int64_t* dst, uint8_t* rev, int64_t* node_label_out,
-                              int64_t* edge_label_out, int64_t* node_graph, int64_t* edge_graph, void* stream) {
+                              int add_reversed, int padded, int64_t* src, int64_t* dst, uint8_t* rev,
+                              int64_t* node_label_out, int64_t* edge_label_out, int64_t* node_graph, int64_t* edge_graph,
+                              void* stream) {
   using namespace dmp;
   DMP_CHECK_ARG(num_selected >= 0 && total_nodes >= 0 && total_edges >= 0, "batch_fill: negative size");
   if (total_nodes + total_edges == 0) return DMP_OK;
@@ -195,7 +212,7 @@ extern "C" int dmp_batch_fill(const int64_t* sel, int64_t num_selected, const in
   BatchFillParams p;
   p.sel = sel; p.B = num_selected; p.noff = node_offsets; p.eoff = edge_offsets; p.u = u; p.v = v;
   p.vlabel = node_label; p.elabel = edge_label; p.new_noff = batch_node_offsets; p.new_eoff = batch_edge_offsets;
-  p.total_nodes = total_nodes; p.total_edges = total_edges; p.reversed = add_reversed;
+  p.total_nodes = total_nodes; p.total_edges = total_edges; p.reversed = add_reversed; p.padded = padded;
   p.src = src; p.dst = dst; p.rev = rev; p.vlabel_out = node_label_out; p.elabel_out = edge_label_out;
   p.node_graph = node_graph; p.edge_graph = edge_graph;
   const int64_t need = (total_nodes + total_edges + kThreads - 1) / kThreads;

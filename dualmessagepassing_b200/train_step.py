@@ -129,17 +129,24 @@ class DevicePairDataset:
         self.counts = put(ds.counts, torch.float32)
 
 
-def batch_on_device(dev_side, sel, sel_host, add_reversed=True):
+def batch_on_device(dev_side, sel, sel_host, add_reversed=True, pad_to=None):
     """Disjoint union of graphs `sel` (device int64 [B]; `sel_host` = the same ids on the host, used only to size
     the outputs) with per-graph reversed-edge blocks, written by two kernels (dmp_batch_offsets + dmp_batch_fill):
     `dgl.batch` + `add_reversed_edges` semantics (dataset.py:1321-1328, train.py:299-327), bit-identical to the host
-    `_collate_side`.  Returns a DMPGraph with the same frames `to_device` produces."""
+    `_collate_side`.  Returns a DMPGraph with the same frames `to_device` produces.
+
+    pad_to = (nodes, edges): fixed output sizes (>= the real totals, nodes > real nodes when any edge is padded); the
+    tail is isolated dummy nodes (graph id B) and self-loops on the last dummy node.  `sel_host` may then be None: the
+    call needs nothing from the host and can be captured in a CUDA graph."""
     from . import _lib
     d = dev_side
     dev = d["u"].device
-    B = int(len(sel_host))
-    tn = int(d["n_host"][sel_host].sum())
-    te = int(d["e_host"][sel_host].sum()) * (2 if add_reversed else 1)
+    B = int(sel.numel())
+    if pad_to is None:
+        tn = int(d["n_host"][sel_host].sum())
+        te = int(d["e_host"][sel_host].sum()) * (2 if add_reversed else 1)
+    else:
+        tn, te = int(pad_to[0]), int(pad_to[1])
     i64 = dict(dtype=torch.int64, device=dev)
     new_noff, new_eoff = torch.empty(B + 1, **i64), torch.empty(B + 1, **i64)
     st = _lib.stream_ptr(dev)
@@ -150,8 +157,8 @@ def batch_on_device(dev_side, sel, sel_host, add_reversed=True):
     vl, el, ng = torch.empty(tn, **i64), torch.empty(te, **i64), torch.empty(tn, **i64)
     _lib.call("dmp_batch_fill", dev, _lib.ptr(sel), B, _lib.ptr(d["noff"]), _lib.ptr(d["eoff"]), _lib.ptr(d["u"]),
               _lib.ptr(d["v"]), _lib.ptr(d["vl"]), _lib.ptr(d["el"]), _lib.ptr(new_noff), _lib.ptr(new_eoff), tn, te,
-              int(add_reversed), _lib.ptr(src), _lib.ptr(dst), _lib.ptr(rev), _lib.ptr(vl), _lib.ptr(el), _lib.ptr(ng),
-              None, st, tag="batch_fill")
+              int(add_reversed), int(pad_to is not None), _lib.ptr(src), _lib.ptr(dst), _lib.ptr(rev), _lib.ptr(vl),
+              _lib.ptr(el), _lib.ptr(ng), None, st, tag="batch_fill")
     g = DMPGraph(src, dst, tn)
     g.edata[REVFLAG] = rev.view(torch.bool)
     g.ndata[NODELABEL] = vl
@@ -206,7 +213,8 @@ class SubgraphCountingModel(nn.Module):
         bsz = pattern.batch_num_nodes().numel()
         # ScalarFilter-style gate (filter.py:6-16, basemodel.py:1394-1423): a graph node/edge passes if its
         # label occurs in the paired pattern
-        pres_v = torch.zeros((bsz, self.num_vlabels), device=graph.device)
+        # (+1 row: padded batches park their dummy nodes in graph id `bsz`, train_step.batch_on_device(pad_to=...))
+        pres_v = torch.zeros((bsz + 1, self.num_vlabels), device=graph.device)
         pres_v[pattern.ndata["graph_id"], pattern.ndata[NODELABEL]] = 1.0
         v_gate = pres_v[graph.ndata["graph_id"], graph.ndata[NODELABEL]]
         p_v, p_e = self._embed(pattern)
@@ -250,6 +258,7 @@ class _SegSum(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         (row_segment,) = ctx.saved_tensors
+        g = torch.cat([g, g.new_zeros((1, g.shape[1]))])     # dummy rows of a padded batch (segment id = #graphs): no gradient
         return g[row_segment], None, None
 
 
@@ -265,3 +274,78 @@ def train_step(model, optimizer, pattern, graph, target, *, world=1, clip=10.0, 
     torch.nn.utils.clip_grad_norm_(model.parameters(), clip, foreach=True)
     optimizer.step()
     return loss
+
+
+class GraphedTrainStep:
+    """The whole training step -- batch construction on the device (row N1), plan build, 3 shared DMP layers on the union
+    of pattern and graph batch, head, MSE, backward, clip, AdamW -- captured ONCE in a CUDA graph and replayed per step:
+    the only host work per step is drawing the pair ids and one 4 KB copy.
+
+    Batches differ in their node / edge totals, so the union is padded to a fixed bucket (mean + 6 sigma of the dataset's
+    per-batch totals, at least one dummy node) with isolated dummy nodes and self-loop dummy edges that no real row ever
+    sees and no pooling includes; a batch that does not fit the bucket (never, at 6 sigma) runs the eager step instead.
+    Needs an optimizer built with `capturable=True`."""
+
+    def __init__(self, model, optimizer, dds, pairs, clip=10.0, warmup=3):
+        self.model, self.opt, self.dds, self.pairs, self.clip = model, optimizer, dds, int(pairs), clip
+        dev = dds.device
+        self.pad = {}
+        for side in ("p", "g"):
+            d = dds.sides[side]
+            n, e2 = d["n_host"].astype(np.float64), 2.0 * d["e_host"].astype(np.float64)
+            pn = pairs * n.mean() + 6.0 * np.sqrt(pairs) * n.std() + 1
+            pe = pairs * e2.mean() + 6.0 * np.sqrt(pairs) * e2.std()
+            self.pad[side] = (int(np.ceil(pn / 64.0)) * 64, int(np.ceil(pe / 64.0)) * 64)
+        self.sel = torch.zeros(self.pairs, dtype=torch.int64, device=dev)
+        self.sel_pinned = torch.zeros(self.pairs, dtype=torch.int64).pin_memory()
+        self.graph = None
+        self.loss = None
+        self.fallbacks = 0
+        # warm-up on a side stream (lazy initialisations: kernel attributes, workspaces, optimizer state), then capture
+        rng = np.random.Generator(np.random.PCG64(0))
+        side_stream = torch.cuda.Stream(device=dev)
+        side_stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side_stream):
+            for _ in range(warmup):
+                self._load(np.sort(rng.choice(dds.num, size=self.pairs, replace=False)))
+                self._body()
+        torch.cuda.current_stream(dev).wait_stream(side_stream)
+        torch.cuda.synchronize(dev)
+        self._load(np.sort(rng.choice(dds.num, size=self.pairs, replace=False)))
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.loss = self._body()
+        self.graph = g
+
+    def _load(self, idx):
+        self.sel_pinned.copy_(torch.from_numpy(np.ascontiguousarray(idx, dtype=np.int64)))
+        self.sel.copy_(self.sel_pinned, non_blocking=True)
+
+    def _body(self):
+        p = batch_on_device(self.dds.sides["p"], self.sel, None, pad_to=self.pad["p"])
+        g = batch_on_device(self.dds.sides["g"], self.sel, None, pad_to=self.pad["g"])
+        y = self.dds.counts[self.sel]
+        self.opt.zero_grad(set_to_none=True)
+        pred = self.model(p, g, union=union_graph(p, g))
+        loss = torch.mean((pred - y) ** 2)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.clip, foreach=True)
+        self.opt.step()
+        return loss
+
+    def fits(self, idx):
+        for side in ("p", "g"):
+            d = self.dds.sides[side]
+            if int(d["n_host"][idx].sum()) + 1 > self.pad[side][0] or 2 * int(d["e_host"][idx].sum()) > self.pad[side][1]:
+                return False
+        return True
+
+    def __call__(self, idx):
+        """One training step on pairs `idx` (host array of length `pairs`); returns the loss tensor (device)."""
+        if not self.fits(idx):
+            self.fallbacks += 1
+            p, g, y, _ = collate_on_device(self.dds, idx)
+            return train_step(self.model, self.opt, p, g, y, clip=self.clip)
+        self._load(idx)
+        self.graph.replay()
+        return self.loss

@@ -270,6 +270,10 @@ DMP_API int dmp_bn_backward(const float* g, int64_t ldg, const float* x, int64_t
  * -- per-graph edge order preserved, exactly dgl.batch of add_reversed_edges'ed graphs; labels gathered alongside
  * (the caller applies `label += max_ngel` on reversed edges, train.py:310); node_graph / edge_graph [total] = owning
  * batch index (may be NULL).  total_nodes / total_edges are host integers (the host keeps the per-graph sizes).
+ * padded != 0: total_nodes / total_edges are FIXED bucket sizes >= the real totals (which the kernel reads from the
+ * offsets, on the device) -- the rest is filled with isolated dummy nodes (graph id B, label 0) and forward self-loops on
+ * the last dummy node: a batch of any composition then has the same shapes and addresses, which is what lets the whole
+ * training step be captured in one CUDA graph (train_step.GraphedTrainStep).
  */
 DMP_API int dmp_batch_offsets(const int64_t* sel, int64_t num_selected, const int64_t* node_offsets,
                               const int64_t* edge_offsets, int add_reversed, int64_t* batch_node_offsets,
@@ -278,8 +282,9 @@ DMP_API int dmp_batch_fill(const int64_t* sel, int64_t num_selected, const int64
                            const int64_t* edge_offsets, const int64_t* u, const int64_t* v, const int64_t* node_label,
                            const int64_t* edge_label, const int64_t* batch_node_offsets,
                            const int64_t* batch_edge_offsets, int64_t total_nodes, int64_t total_edges,
-                           int add_reversed, int64_t* src, int64_t* dst, uint8_t* rev, int64_t* node_label_out,
-                           int64_t* edge_label_out, int64_t* node_graph, int64_t* edge_graph, void* stream);
+                           int add_reversed, int padded, int64_t* src, int64_t* dst, uint8_t* rev,
+                           int64_t* node_label_out, int64_t* edge_label_out, int64_t* node_graph, int64_t* edge_graph,
+                           void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Ragged <-> padded (row N2): `split_and_batchify_graph_feats(batched_graph_feats, graph_sizes, pre_pad)`

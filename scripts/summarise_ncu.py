@@ -19,7 +19,7 @@ for row in csv.DictReader(io.StringIO("".join(lines))):
     v = v / 1e6 if u.startswith("n") else v / 1e3 if u.startswith("u") else v * 1e3 if u in ("second", "s") else v
     k = row["Kernel Name"].split("(")[0][:100]
     a = agg.setdefault(k, [0, 0.0]); a[0] += 1; a[1] += v; total += v; n += 1
-md = ["# ncu summary (round 1)", "", "Source: `%s` (launch list, `--metrics gpu__time_duration.sum --clock-control none`) and `%s` (`--set full`)." % (launch_csv, rep),
+md = ["# ncu summary (round 2)", "", "Source: `%s` (launch list, `--metrics gpu__time_duration.sum --clock-control none`) and `%s` (`--set full`)." % (launch_csv, rep),
       "Per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes.", "",
       "## Launch list: %d launches, %.1f ms total" % (n, total), "", "| kernel | launches | total ms | share |", "|---|---:|---:|---:|"]
 for k, (c, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:18]:
