@@ -67,6 +67,7 @@ def parse():
     ap.add_argument("--no-train", action="store_true", help="skip the secondary train graphs/sec measurement")
     ap.add_argument("--no-mlp0", action="store_true", help="skip the num_mlp_layers=0 variant of the layer")
     ap.add_argument("--train-config", default="all", choices=["all", "cfg1", "cfg2", "cfg3"])
+    ap.add_argument("--no-train-graph", action="store_true", help="run the training step eagerly instead of as a CUDA graph")
     ap.add_argument("--no-cfg4", action="store_true", help="skip the UNC encoder (BASELINE configs[3]) measurement")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the eager-torch GPU comparator")
     ap.add_argument("--train-steps", type=int, default=30)
@@ -457,7 +458,7 @@ def run_train(args, dev, world, rank, config, hbm_peak):
     ds = ts.SyntheticPairDataset(config, num=4 * cfg["pairs"], seed=2000 + rank)
     torch.manual_seed(2000)
     model = ts.SubgraphCountingModel(cfg["hidden"], cfg["labels"][0], cfg["labels"][1]).to(dev)
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, amsgrad=True)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, amsgrad=True, capturable=True)
     rng = np.random.Generator(np.random.PCG64(7 + rank))
     h2d = 0
     alg = [0, 0]     # sparse-core algorithmic bytes (4H(9E+4N)+2I per layer fwd+bwd), steps counted
@@ -466,15 +467,27 @@ def run_train(args, dev, world, rank, config, hbm_peak):
     # device by two kernels; the host only draws the pair ids (4 KB H2D per step).  The reference collates on the CPU
     # main process and copies the batched graph every step (dataset.py:1604-1611, train.py:606-608).
     dds = ts.DevicePairDataset(ds, dev)
+    # ... and the whole step (batch construction, plan build, 3 shared layers on the union graph, head, loss, backward,
+    # gradient all-reduce, clip, AdamW) is ONE CUDA-graph replay per step (train_step.GraphedTrainStep): the host draws the
+    # pair ids and copies 4 KB.  --no-train-graph runs the same step eagerly (A/B).
+    graphed, graph_err = None, None
+    if not args.no_train_graph:
+        try:
+            graphed = ts.GraphedTrainStep(model, opt, dds, cfg["pairs"], world=world)
+        except Exception as exc:      # e.g. a collective that cannot be captured: fall back to the eager step, and say so
+            graph_err = "%s: %s" % (type(exc).__name__, str(exc)[:200])
 
     def one_step():
         nonlocal h2d
         idx = np.sort(rng.choice(ds.num, size=cfg["pairs"], replace=False))
-        p, g, y, h2d = ts.collate_on_device(dds, idx)
-        N = p.number_of_nodes() + g.number_of_nodes()
-        E = p.number_of_edges() + g.number_of_edges()
+        N = int(dds.sides["p"]["n_host"][idx].sum() + dds.sides["g"]["n_host"][idx].sum())
+        E = 2 * int(dds.sides["p"]["e_host"][idx].sum() + dds.sides["g"]["e_host"][idx].sum())
         alg[0] += 3 * (4 * cfg["hidden"] * (9 * E + 4 * N) + 2 * (17 * E + 12 * (N + 1)))
         alg[1] += 1
+        if graphed is not None:
+            h2d = idx.nbytes
+            return graphed(idx)
+        p, g, y, h2d = ts.collate_on_device(dds, idx)
         return ts.train_step(model, opt, p, g, y, world=world)
 
     for _ in range(5):
@@ -498,6 +511,10 @@ def run_train(args, dev, world, rank, config, hbm_peak):
             "scaling": "weak", "config": "BASELINE configs[%d] (%s): 3 shared DMP layers, hidden %d, sum-pool head, "
             "MSE, AdamW(amsgrad)" % ({"cfg1": 0, "cfg2": 1, "cfg3": 2}[config], config, cfg["hidden"]),
             "h2d_bytes_per_step": int(h2d), "dmp_launches_per_step": (_lib.LAUNCHES - l0) / args.train_steps,
+            "cuda_graph": None if graphed is None else {
+                "replays_per_step": 1, "dmp_kernels_in_graph": graphed.dmp_kernels_in_graph,
+                "padded_union": {k: list(v) for k, v in graphed.pad.items()}, "eager_fallbacks": graphed.fallbacks},
+            "cuda_graph_error": graph_err,
             "hbm": {"sparse_core_alg_bytes_per_step": bytes_per_step, "frac": bytes_per_step / sec / 1e9 / hbm_peak,
                     "note": "whole working set <= 0.4 GB: launch/latency-bound regime (SURVEY 7.2), not a bandwidth claim"},
             "final_loss": float(loss.item())}

@@ -215,7 +215,8 @@ class SubgraphCountingModel(nn.Module):
         # label occurs in the paired pattern
         # (+1 row: padded batches park their dummy nodes in graph id `bsz`, train_step.batch_on_device(pad_to=...))
         pres_v = torch.zeros((bsz + 1, self.num_vlabels), device=graph.device)
-        pres_v[pattern.ndata["graph_id"], pattern.ndata[NODELABEL]] = 1.0
+        pres_v.index_put_((pattern.ndata["graph_id"], pattern.ndata[NODELABEL]),
+                          torch.ones((), device=graph.device))     # (a device scalar: capturable in a CUDA graph)
         v_gate = pres_v[graph.ndata["graph_id"], graph.ndata[NODELABEL]]
         p_v, p_e = self._embed(pattern)
         g_v, g_e = self._embed(graph)
@@ -286,8 +287,10 @@ class GraphedTrainStep:
     sees and no pooling includes; a batch that does not fit the bucket (never, at 6 sigma) runs the eager step instead.
     Needs an optimizer built with `capturable=True`."""
 
-    def __init__(self, model, optimizer, dds, pairs, clip=10.0, warmup=3):
+    def __init__(self, model, optimizer, dds, pairs, clip=10.0, warmup=3, world=1):
+        from . import _lib
         self.model, self.opt, self.dds, self.pairs, self.clip = model, optimizer, dds, int(pairs), clip
+        self.world = world            # > 1: the flat-buffer gradient all-reduce (NCCL) is captured with the step
         dev = dds.device
         self.pad = {}
         for side in ("p", "g"):
@@ -305,17 +308,22 @@ class GraphedTrainStep:
         rng = np.random.Generator(np.random.PCG64(0))
         side_stream = torch.cuda.Stream(device=dev)
         side_stream.wait_stream(torch.cuda.current_stream(dev))
+        self.warmup_ids = []          # the warm-up steps are real optimizer steps: recorded so that a run can be reproduced
         with torch.cuda.stream(side_stream):
-            for _ in range(warmup):
-                self._load(np.sort(rng.choice(dds.num, size=self.pairs, replace=False)))
+            for _ in range(max(int(warmup), 1)):     # >= 1: optimizer state must exist before capture, or its
+                ids = np.sort(rng.choice(dds.num, size=self.pairs, replace=False))   # zero-initialisation is replayed
+                self.warmup_ids.append(ids)
+                self._load(ids)
                 self._body()
         torch.cuda.current_stream(dev).wait_stream(side_stream)
         torch.cuda.synchronize(dev)
         self._load(np.sort(rng.choice(dds.num, size=self.pairs, replace=False)))
         g = torch.cuda.CUDAGraph()
+        l0 = _lib.LAUNCHES
         with torch.cuda.graph(g):
             self.loss = self._body()
         self.graph = g
+        self.dmp_kernels_in_graph = _lib.LAUNCHES - l0     # C-ABI launches recorded into the graph (replayed, not re-issued)
 
     def _load(self, idx):
         self.sel_pinned.copy_(torch.from_numpy(np.ascontiguousarray(idx, dtype=np.int64)))
@@ -329,6 +337,9 @@ class GraphedTrainStep:
         pred = self.model(p, g, union=union_graph(p, g))
         loss = torch.mean((pred - y) ** 2)
         loss.backward()
+        if self.world > 1:
+            from .parallel import allreduce_gradients
+            allreduce_gradients(self.model.parameters(), average=True)
         torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.clip, foreach=True)
         self.opt.step()
         return loss
@@ -345,7 +356,7 @@ class GraphedTrainStep:
         if not self.fits(idx):
             self.fallbacks += 1
             p, g, y, _ = collate_on_device(self.dds, idx)
-            return train_step(self.model, self.opt, p, g, y, clip=self.clip)
+            return train_step(self.model, self.opt, p, g, y, world=self.world, clip=self.clip)
         self._load(idx)
         self.graph.replay()
         return self.loss

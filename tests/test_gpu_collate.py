@@ -60,6 +60,66 @@ def test_train_step_on_device_batches_matches_host_batches():
 
 
 @pytest.mark.gpu
+def test_padded_device_batch_has_fixed_shapes_and_inert_padding():
+    """pad_to: the real part equals the unpadded batch, the tail is isolated dummy nodes (graph id B) + self-loops on the
+    last dummy node; the model's prediction on a padded batch equals the unpadded one."""
+    from dualmessagepassing_b200 import train_step as ts
+    from dualmessagepassing_b200.constants import EDGELABEL, NODELABEL, REVFLAG
+    ds = ts.SyntheticPairDataset("cfg1", num=120, seed=4)
+    dds = ts.DevicePairDataset(ds, "cuda")
+    idx = np.arange(10, 74)
+    sel = torch.from_numpy(idx).cuda()
+    real = ts.batch_on_device(dds.sides["g"], sel, idx)
+    N, E = real.number_of_nodes(), real.number_of_edges()
+    padded = ts.batch_on_device(dds.sides["g"], sel, None, pad_to=(N + 37, E + 200))
+    assert padded.number_of_nodes() == N + 37 and padded.number_of_edges() == E + 200
+    (s0, d0), (s1, d1) = real.all_edges(), padded.all_edges()
+    assert torch.equal(s1[:E], s0) and torch.equal(d1[:E], d0)
+    assert bool((s1[E:] == N + 36).all()) and bool((d1[E:] == N + 36).all()) and not bool(padded.edata[REVFLAG][E:].any())
+    for key, frame in ((NODELABEL, "ndata"), ("graph_id", "ndata"), (EDGELABEL, "edata")):
+        a, b = getattr(real, frame)[key], getattr(padded, frame)[key]
+        assert torch.equal(b[:a.numel()], a)
+    assert bool((padded.ndata["graph_id"][N:] == 64).all())
+    assert torch.equal(padded.batch_num_nodes(), real.batch_num_nodes())
+    torch.manual_seed(0)
+    model = ts.SubgraphCountingModel(64, 1, 1).cuda()
+    p = ts.batch_on_device(dds.sides["p"], sel, idx)
+    p_pad = ts.batch_on_device(dds.sides["p"], sel, None, pad_to=(p.number_of_nodes() + 5, p.number_of_edges() + 64))
+    a = model(p, real, union=ts.union_graph(p, real))
+    b = model(p_pad, padded, union=ts.union_graph(p_pad, padded))
+    torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.gpu
+def test_graphed_train_step_matches_eager_step():
+    """The CUDA-graphed step (device batching + fwd + bwd + clip + AdamW in one replay) follows the eager step's loss
+    trajectory on the same pair ids."""
+    import copy
+    from dualmessagepassing_b200 import _lib, train_step as ts
+    ds = ts.SyntheticPairDataset("cfg1", num=256, seed=6)
+    dds = ts.DevicePairDataset(ds, "cuda")
+    torch.manual_seed(0)
+    model = ts.SubgraphCountingModel(64, 1, 1).cuda()
+    ref = copy.deepcopy(model)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, amsgrad=True, capturable=True)
+    opt_ref = torch.optim.AdamW(ref.parameters(), lr=1e-3, amsgrad=True, capturable=True)
+    rng = np.random.Generator(np.random.PCG64(1))
+    batches = [np.sort(rng.choice(256, size=64, replace=False)) for _ in range(6)]
+    graphed = ts.GraphedTrainStep(model, opt, dds, 64, warmup=2)
+    l0 = _lib.LAUNCHES
+    got = [float(graphed(b)) for b in batches]
+    assert _lib.LAUNCHES == l0 and graphed.fallbacks == 0            # replays only: no C-ABI call from the host
+    want = []
+    for b in graphed.warmup_ids:                                     # the warm-up steps were real optimizer steps
+        p, g, y, _ = ts.collate_on_device(dds, b)
+        ts.train_step(ref, opt_ref, p, g, y)
+    for b in batches:
+        p, g, y, _ = ts.collate_on_device(dds, b)
+        want.append(float(ts.train_step(ref, opt_ref, p, g, y)))
+    np.testing.assert_allclose(got, want, rtol=2e-3)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("pre_pad", [False, True])
 @pytest.mark.parametrize("H", [1, 50, 128])
 def test_ragged_pad_matches_reference_loop(pre_pad, H):
