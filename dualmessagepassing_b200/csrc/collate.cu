@@ -84,9 +84,13 @@ __global__ void __launch_bounds__(kThreads) batch_fill_kernel(const BatchFillPar
       if (p.node_graph) p.node_graph[t] = i;
     } else {
       const int64_t k = t - p.total_nodes;
-      if (k >= real_edges) {          // padding: a forward self-loop on the LAST (dummy) node -- touches no real row
-        p.src[k] = p.total_nodes - 1;
-        p.dst[k] = p.total_nodes - 1;
+      if (k >= real_edges) {          // padding: forward self-loops spread round-robin over the dummy nodes -- they touch
+                                      // no real row, and no dummy node becomes a hub (a 15 k-edge segment would
+                                      // serialise one lane group of every segment reduce for ~1 ms)
+        const int64_t dummies = p.total_nodes - real_nodes;      // >= 1 whenever an edge is padded (caller's contract)
+        const int64_t node = real_nodes + (k - real_edges) % (dummies > 0 ? dummies : 1);
+        p.src[k] = node;
+        p.dst[k] = node;
         if (p.rev) p.rev[k] = 0;
         if (p.elabel_out) p.elabel_out[k] = 0;
         if (p.edge_graph) p.edge_graph[k] = p.B;

@@ -136,7 +136,7 @@ def batch_on_device(dev_side, sel, sel_host, add_reversed=True, pad_to=None):
     `_collate_side`.  Returns a DMPGraph with the same frames `to_device` produces.
 
     pad_to = (nodes, edges): fixed output sizes (>= the real totals, nodes > real nodes when any edge is padded); the
-    tail is isolated dummy nodes (graph id B) and self-loops on the last dummy node.  `sel_host` may then be None: the
+    tail is dummy nodes (graph id B) and self-loops spread round-robin over them.  `sel_host` may then be None: the
     call needs nothing from the host and can be captured in a CUDA graph."""
     from . import _lib
     d = dev_side
@@ -283,7 +283,7 @@ class GraphedTrainStep:
     the only host work per step is drawing the pair ids and one 4 KB copy.
 
     Batches differ in their node / edge totals, so the union is padded to a fixed bucket (mean + 6 sigma of the dataset's
-    per-batch totals, at least one dummy node) with isolated dummy nodes and self-loop dummy edges that no real row ever
+    per-batch totals, at least one dummy node) with dummy nodes and self-loop dummy edges that no real row ever
     sees and no pooling includes; a batch that does not fit the bucket (never, at 6 sigma) runs the eager step instead.
     Needs an optimizer built with `capturable=True`."""
 

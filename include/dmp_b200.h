@@ -271,8 +271,8 @@ DMP_API int dmp_bn_backward(const float* g, int64_t ldg, const float* x, int64_t
  * (the caller applies `label += max_ngel` on reversed edges, train.py:310); node_graph / edge_graph [total] = owning
  * batch index (may be NULL).  total_nodes / total_edges are host integers (the host keeps the per-graph sizes).
  * padded != 0: total_nodes / total_edges are FIXED bucket sizes >= the real totals (which the kernel reads from the
- * offsets, on the device) -- the rest is filled with isolated dummy nodes (graph id B, label 0) and forward self-loops on
- * the last dummy node: a batch of any composition then has the same shapes and addresses, which is what lets the whole
+ * offsets, on the device) -- the rest is filled with dummy nodes (graph id B, label 0) and forward self-loops spread
+ * round-robin over them (total_nodes must exceed the real node count when any edge is padded): a batch of any composition then has the same shapes and addresses, which is what lets the whole
  * training step be captured in one CUDA graph (train_step.GraphedTrainStep).
  */
 DMP_API int dmp_batch_offsets(const int64_t* sel, int64_t num_selected, const int64_t* node_offsets,
