@@ -313,6 +313,33 @@ def run_cfg4(dev, hbm_peak, steps=20):
     torch.cuda.synchronize()
     launches = (_lib.LAUNCHES - l0) / steps
     ms = float(np.median([a.elapsed_time(b) for a, b in evs]))
+    # the same step as ONE CUDA-graph replay (full-graph training repeats the same shapes every step: the ~80 C-ABI
+    # launches + torch glue of a 5 ms step are launch-latency, not work)
+    graph_ms, graph_err = None, None
+    try:
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        cg = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(cg):
+            step()
+        cg.replay()
+        gevs = []
+        for _ in range(steps):
+            flush.zero_()
+            e0_, e1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0_.record()
+            cg.replay()
+            e1_.record()
+            gevs.append((e0_, e1_))
+        torch.cuda.synchronize()
+        graph_ms = float(np.median([a.elapsed_time(b) for a, b in gevs]))
+        del cg
+    except Exception as exc:
+        graph_err = "%s: %s" % (type(exc).__name__, str(exc)[:200])
     # one profiled step: which hand-written kernels ran, and the bytes the GEMM launches report
     _lib.PROFILE = []
     step()
@@ -332,10 +359,12 @@ def run_cfg4(dev, hbm_peak, steps=20):
                         "BatchNorm, Tanh/None) + relation mean pooling, hidden %d (zero-padded to 64 for the tcgen05 "
                         "kernels), full-graph fwd+bwd" % (E, h),
             "ms_per_step": ms, "value": 2 * E / (ms * 1e-3), "unit": "edges/s (edges x layers per second)",
+            "cuda_graph": {"ms_per_step": graph_ms, "value": None if graph_ms is None else 2 * E / (graph_ms * 1e-3),
+                           "error": graph_err, "what": "the same fwd+bwd captured once and replayed (1 launch per step)"},
             "steps": steps, "l2": "L2 flushed (256 MB write) before every timed step; median of per-step CUDA-event times",
             "dmp_launches_per_step": launches,
             "hbm": {"sparse_core_alg_bytes": sparse, "dense_launch_bytes": dense,
-                    "frac": (sparse + dense) / (ms * 1e-3) / 1e9 / hbm_peak,
+                    "frac": (sparse + dense) / ((graph_ms or ms) * 1e-3) / 1e9 / hbm_peak,
                     "note": "launch-latency regime: %d launches of ~10-30 us kernels per step" % round(launches)},
             "kernels": {k: {"launches": v[0], "ms": v[1]} for k, v in sorted(tags.items(), key=lambda kv: -kv[1][1])}}
 

@@ -71,21 +71,36 @@ class DMPNNRepNet(nn.Module):
         return self._loop(graph, v, e, vg, eg)
 
 
+_rel_index_cache = {}
+
+
+def _relation_index(rel, num_rels):
+    """(position order, int32 indptr, counts) of the relation ids, cached per tensor: the edge types of a graph do not
+    change between steps, and keeping the sort / bincount (which synchronise) out of the step makes it capturable."""
+    key = (rel.data_ptr(), rel._version, int(rel.numel()), int(num_rels), str(rel.device))
+    hit = _rel_index_cache.get(key)
+    if hit is None:
+        r = rel.reshape(-1).to(torch.int64)
+        order = torch.argsort(r, stable=True)
+        counts = torch.bincount(r, minlength=num_rels)
+        indptr = torch.zeros(num_rels + 1, dtype=torch.int32, device=rel.device)
+        indptr[1:] = torch.cumsum(counts, 0)
+        if len(_rel_index_cache) > 8:
+            _rel_index_cache.clear()
+        hit = _rel_index_cache[key] = (order.to(torch.int32), indptr, counts, rel)   # rel kept alive: the key is its address
+    return hit
+
+
 class _RelationPool(torch.autograd.Function):
     @staticmethod
     def forward(ctx, z, rel, num_rels):
         _lib.require_cuda(z, rel)
-        rel = rel.reshape(-1).to(torch.int64)
-        order = torch.argsort(rel, stable=True)
-        counts = torch.bincount(rel, minlength=num_rels)
-        indptr = torch.zeros(num_rels + 1, dtype=torch.int32, device=z.device)
-        indptr[1:] = torch.cumsum(counts, 0)
+        order, indptr, counts, _ = _relation_index(rel, num_rels)
         # num_rels segments of ~E/num_rels rows each: chunked so that the whole GPU works on them (the reference's
         # `masked_fill(...).sum(dim=0)` has no sequential order to preserve)
-        sums = segment_reduce_two_level(indptr, order.to(torch.int32), z, z.shape[1], chunk=512,
-                                        tag="segment_reduce.rel_pool")
+        sums = segment_reduce_two_level(indptr, order, z, z.shape[1], chunk=512, tag="segment_reduce.rel_pool")
         denom = counts.to(z.dtype) + 1e-8
-        ctx.save_for_backward(rel, denom)
+        ctx.save_for_backward(rel.reshape(-1).to(torch.int64), denom)
         return sums / denom.unsqueeze(-1)
 
     @staticmethod
