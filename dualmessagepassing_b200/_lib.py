@@ -19,6 +19,7 @@ SEG_NEGATE_OUT = 2
 SEG_ONLY_FWD = 4
 SEG_ONLY_REV = 8
 SEG_SPLIT_BY_REV = 16
+SEG_SHORT = 32
 ORDER_SCM = 0
 ORDER_UNC = 1
 EDGE_MIRRORED_HALVES = 16
@@ -43,8 +44,6 @@ SIGNATURES = {
     "dmp_edge_backward": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _i64, _vp],
     "dmp_gate_residual": [_vp, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i32, _f32, _vp],
     "dmp_gate_residual_backward": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _i32, _f32, _vp],
-    "dmp_gemm_tf32x3_acc_gather": [_vp, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp,
-                                   _i64, _vp],
     "dmp_gemm_tn_workspace_bytes": [_i64, _i64, ctypes.POINTER(ctypes.c_int64)],
     "dmp_gemm_tn_tf32x3": [_vp, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _i32, _vp, _i64, _vp],
     "dmp_gemm_tf32x3": [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _i32, _f32, _vp],

@@ -33,8 +33,12 @@ struct SegParams {
 
 // KIND: 0 plain, 1 FILTER (keep only forward / only reversed edges), 2 SPLIT (two sums per segment: forward edges into
 // out[:, 0:H], reversed edges into out[:, H:2H] -- the aggregate-first form of the node update reads every row once)
-template <int VEC, int G, int ITER, int U, int KIND>
-__global__ void __launch_bounds__(kThreads, 3) segment_reduce_kernel(const SegParams p) {
+// MINB: resident CTAs per SM the register allocation must allow.  Long segments want U = 8 rows in flight per lane
+// (80 registers, 3 CTAs); SHORT segments (a destination-range partition leaves ~2.5 local edges per global a-/b-segment)
+// are bound by the indptr -> eid -> row latency chain of one segment per warp, so the DMP_SEG_SHORT variant keeps U = 2
+// rows in flight and fits twice the warps (same adds in the same order: identical bits).
+template <int VEC, int G, int ITER, int U, int KIND, int MINB = 3>
+__global__ void __launch_bounds__(kThreads, MINB) segment_reduce_kernel(const SegParams p) {
   constexpr int kGroups = kThreads / G;
   constexpr bool FILTER = (KIND == 1), SPLIT = (KIND == 2);
   const int lane = threadIdx.x % G;
@@ -153,6 +157,12 @@ static int launch(const SegParams& p, cudaStream_t stream) {
   if (blocks > 0x7fffffffLL) {
     set_error("segment_reduce: too many segments (%lld)", (long long)p.nseg);
     return DMP_ERR_UNSUPPORTED;
+  }
+  if constexpr (VEC == 4 && G == 32 && ITER == 1) {
+    if ((p.mode & DMP_SEG_SHORT) && !(p.mode & DMP_SEG_SPLIT_BY_REV) && !filter) {
+      segment_reduce_kernel<VEC, G, ITER, 2, 0, 6><<<(unsigned)blocks, kThreads, 0, stream>>>(p);
+      return launch_status("segment_reduce_kernel<short>");
+    }
   }
   if (p.mode & DMP_SEG_SPLIT_BY_REV) segment_reduce_kernel<VEC, G, ITER, U, 2><<<(unsigned)blocks, kThreads, 0, stream>>>(p);
   else if (filter) segment_reduce_kernel<VEC, G, ITER, U, 1><<<(unsigned)blocks, kThreads, 0, stream>>>(p);

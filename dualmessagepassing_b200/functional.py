@@ -329,30 +329,6 @@ def gemm_tn_tf32x3(X, G, *, row_scale=None, out=None, accumulate=False, colsum_x
     return out
 
 
-def gemm_tf32x3_acc_gather(A, Wt, out, *, dst32, tab_fwd, tab_rev=None, rev=None, norm=None, row_scale=None):
-    """out += (row_scale ⊙ A) @ Wt.T + sgn * norm * tab_{rev}[dst32]  (sgn = +1 on reversed edges, -1 otherwise):
-    the gradient of the node aggregation w.r.t. the edge states, gathered from node-sized tables inside the GEMM
-    epilogue instead of being materialised as an [E,H] tensor.  Raw, in place on `out`."""
-    _lib.require_cuda(A, Wt, out, tab_fwd, tab_rev, dst32, rev, norm, row_scale)
-    A, lda = _lib.row_major(A)
-    Wt, ldb = _lib.row_major(Wt)
-    tab_fwd, ld_tab = _lib.row_major(tab_fwd)
-    if tab_rev is not None:
-        tab_rev, ld2 = _lib.row_major(tab_rev)
-        if ld2 != ld_tab:
-            raise ValueError("tab_fwd and tab_rev must share a leading dimension")
-    M, K = A.shape
-    N = Wt.shape[0]
-    _, ldd = _lib.row_major(out)
-    if row_scale is not None:
-        row_scale = row_scale.reshape(-1).contiguous()
-    _lib.call("dmp_gemm_tf32x3_acc_gather", A.device, _lib.ptr(A), lda, _lib.ptr(row_scale), _lib.ptr(Wt), ldb,
-              _lib.ptr(out), ldd, M, N, K, _lib.ptr(dst32), _lib.ptr(rev), _lib.ptr(norm), _lib.ptr(tab_fwd),
-              _lib.ptr(tab_rev), ld_tab, _stream(A), tag="gemm_tf32x3.acc_gather",
-              nbytes=4 * (M * K + 3 * M * N + N * K) + 9 * M)
-    return out
-
-
 def gemm_tf32x3_dual(A, W1t, W2t, *, row_scale=None, mode="store", out=None, out2=None):
     """Two projections of the same streamed operand in ONE pass (dmp_gemm_tf32x3_dual):
         "store"       out  = A @ W1t.T + row_scale ⊙ (A @ W2t.T)

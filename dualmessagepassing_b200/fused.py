@@ -404,8 +404,9 @@ class _FusedDMPLayer(torch.autograd.Function):
             X_v_full = ctx.X_v_full
 
         # ---- sparse core backward: two sorted-segment sums of gE, one gather of gN ------
-        dQd = segment_reduce(plan.a_indptr, plan.a_eid, gE, H, plan=plan, tag="segment_reduce.dQd_bwd")
-        dQs = segment_reduce(plan.b_indptr, plan.b_eid, gE, H, plan=plan, mode=_lib.SEG_NEGATE_OUT,
+        short = _lib.SEG_SHORT if E < 6 * plan.N else 0     # few rows per segment (partitioned graph): high-occupancy variant
+        dQd = segment_reduce(plan.a_indptr, plan.a_eid, gE, H, plan=plan, mode=short, tag="segment_reduce.dQd_bwd")
+        dQs = segment_reduce(plan.b_indptr, plan.b_eid, gE, H, plan=plan, mode=_lib.SEG_NEGATE_OUT | short,
                              tag="segment_reduce.dQs_bwd")
         w_sd = src_w - dst_w
         Din = in_w.shape[0]

@@ -55,6 +55,10 @@ extern "C" {
                                    sum_e s_e n_e (X_e W) = (sum_e s_e n_e X_e) W  (dmpnn.py:113-133) this replaces the
                                    edge-sized projection by two node-sized ones. */
 
+#define DMP_SEG_SHORT 32 /* hint: segments hold only a few rows on average (destination-range partition: ~2.5 local edges
+                            per global segment): a higher-occupancy variant with fewer rows in flight per lane.  Same
+                            additions in the same order -- results are bit-identical with or without the hint. */
+
 /* dmp_edge_update order */
 #define DMP_ORDER_SCM 0 /* ((eloop + add) + agg) + ebias   dmpnn.py:147-149  */
 #define DMP_ORDER_UNC 1 /* ((eloop + agg) + add) + ebias   model.py:257-259  */
@@ -181,9 +185,9 @@ DMP_API int dmp_gate_residual_backward(const float* gout, int64_t ld_gout, const
  *                                                                 nn.Linear layout ([out, in], row-major)
  * Replaces the per-edge `th.matmul(...)` calls of dmpnn.py:112-113,120-121,146-147 and the MLP Linears
  * (dmpnn.py:45-52) and their autograd transposes.  row_scale [M] (may be NULL) multiplies each row of A
- * first, as a separately rounded fp32 product (fuses `coef ⊙ gE`); with DMP_EPI_ACCUMULATE and N = 128 the same
- * factor is applied to the accumulated row instead (D[r,:] += row_scale[r] * (A[r,:]·Bt^T): equal up to fp32
- * rounding, and the streaming side of the kernel keeps its copy-only fast path).  epilogue = DMP_ACT_* id, optionally
+ * first, as a separately rounded fp32 product (fuses `coef ⊙ gE`); with DMP_EPI_ACCUMULATE the same factor is applied
+ * to the accumulated row instead (D[r,:] += row_scale[r] * (A[r,:]·Bt^T): equal up to fp32 rounding).  The three
+ * products of the split are issued cross terms first (the tensor core's fp32 accumulator truncates: DESIGN.md 4.1).  epilogue = DMP_ACT_* id, optionally
  * OR-ed with DMP_EPI_MUL_ACT_GRAD (D = acc * act'(aux), aux = activation OUTPUT [M,N]) and/or
  * DMP_EPI_ACCUMULATE (D += result).  bias [N] may be NULL.  D must not alias A.
  */
@@ -209,14 +213,6 @@ DMP_API int dmp_gemm_tf32x3(const float* A, int64_t lda, const float* row_scale,
 DMP_API int dmp_gemm_tf32x3_dual(const float* A, int64_t lda, const float* W1t, const float* W2t, int64_t ldw,
                                  const float* row_scale, float* D, int64_t ldd, float* D2, int64_t ldd2,
                                  int64_t M, int64_t N, int64_t K, int mode, void* stream);
-
-/* Backward of `fn.sum` folded into the edge-gradient projection (no [E,H] message-gradient tensor is materialised):
- *   D[r,:] += (row_scale ⊙ A)[r,:] · Bt^T + sgn_r * norm_r * tab_{rev_r}[dst32[r], :]      sgn_r = rev[r] ? +1 : -1
- * with tab_fwd = gN·W_in^T, tab_rev = gN·W_out^T (node-sized).  rev / norm / row_scale may be NULL. */
-DMP_API int dmp_gemm_tf32x3_acc_gather(const float* A, int64_t lda, const float* row_scale, const float* Bt,
-                                       int64_t ldb, float* D, int64_t ldd, int64_t M, int64_t N, int64_t K,
-                                       const int32_t* dst32, const uint8_t* rev, const float* norm,
-                                       const float* tab_fwd, const float* tab_rev, int64_t ld_tab, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Weight-gradient reduction on the tensor cores (3xTF32 split, fp32-level accuracy):

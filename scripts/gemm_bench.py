@@ -1,29 +1,44 @@
-"""Micro-benchmark: dmp_gemm_tf32x3 vs cuBLAS sgemm on the edge-sized projection shape."""
-import sys, torch
+"""Projection kernels at config-5 size (E = 40 M rows, 128 x 128): CUDA-event time per launch, fraction of the measured HBM
+peak, error vs fp64 on a sample.  `DMP_V3_LO=n python scripts/gemm_bench.py` sweeps the hi/lo ring split."""
+import json, os, sys, torch
 sys.path.insert(0, ".")
 from dualmessagepassing_b200 import functional as F
-E = int(sys.argv[1]) if len(sys.argv) > 1 else 8_000_000
-for (N, K) in [(128, 128), (64, 64)]:
-    A = torch.randn(E, K, device="cuda"); Wt = torch.randn(N, K, device="cuda") / 4
-    out = torch.empty(E, N, device="cuda")
-    def t(fn, n=10):
-        fn(); fn(); torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
-        e0.record()
-        for _ in range(n): fn()
-        e1.record(); torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / n
-    G = torch.randn(E, N, device="cuda")
-    ms_rc = t(lambda: A.t() @ G); ms_ro = t(lambda: F.gemm_tn_tf32x3(A, G))
-    refr = A.double().t() @ G.double()
-    er = lambda x: float((x.double() - refr).abs().max() / refr.abs().max())
-    print("   reduction X^T G: cuBLAS %.3f ms (err %.2g) | tf32x3 %.3f ms (%.0f GB/s, err %.2g)" % (
-        ms_rc, er(A.t() @ G), ms_ro, (E * K + E * N) * 4 / 1e6 / ms_ro, er(F.gemm_tn_tf32x3(A, G))))
-    ms_c = t(lambda: torch.mm(A, Wt.t(), out=out))
-    ms_o = t(lambda: F.gemm_tf32x3(A, Wt, out=out))
-    gb = (E * K + E * N) * 4 / 1e9
-    ref = A[:100000].double() @ Wt.double().t()
-    err = lambda x: float((x.double() - ref).abs().max() / ref.abs().max())
-    print("N=%d K=%d E=%d  cuBLAS sgemm %.3f ms (%.0f GB/s, %.1f TF/s, err %.2g) | tf32x3 %.3f ms (%.0f GB/s, %.1f eff TF/s, err %.2g)"
-          % (N, K, E, ms_c, gb / ms_c * 1e3, 2.0 * E * N * K / ms_c / 1e9, err(torch.mm(A[:100000], Wt.t())),
-             ms_o, gb / ms_o * 1e3, 2.0 * E * N * K / ms_o / 1e9, err(F.gemm_tf32x3(A[:100000], Wt))))
+
+E, H = int(sys.argv[1]) if len(sys.argv) > 1 else 40_000_000, 128
+dev = torch.device("cuda")
+A, G = torch.randn(E, H, device=dev), torch.randn(E, H, device=dev)
+D = torch.empty(E, H, device=dev)
+W1, W2 = torch.randn(H, H, device=dev) / 8, torch.randn(H, H, device=dev) / 8
+c = torch.rand(E, device=dev) * 6
+bias = torch.randn(H, device=dev)
+peak = json.load(open("MEASURED_PEAKS.json"))["hbm_gbs"]
+row = 4 * H * E
+
+
+def timed(fn, reps=5):
+    fn(); torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+cases = {
+    "store": (lambda: F.gemm_tf32x3(A, W1, out=D), 2 * row),
+    "bias_act": (lambda: F.gemm_tf32x3(A, W1, bias=bias, act="leaky_relu", slope=0.18, out=D), 2 * row),
+    "grad": (lambda: F.gemm_tf32x3(A, W1, act="leaky_relu", slope=0.18, aux=G, mul_act_grad=True, out=D), 3 * row),
+    "dual.store": (lambda: F.gemm_tf32x3_dual(A, W1, W2, row_scale=c, mode="store", out=D), 2 * row),
+    "dual.accumulate": (lambda: F.gemm_tf32x3_dual(A, W1, W2, row_scale=c, mode="accumulate", out=D), 3 * row),
+    "tn": (lambda: F.gemm_tn_tf32x3(A, G), 2 * row),
+}
+out = {"rows": E, "DMP_V3_LO": os.environ.get("DMP_V3_LO", "default")}
+for name, (fn, nbytes) in cases.items():
+    ms = timed(fn)
+    out[name] = {"ms": round(ms, 3), "frac": round(nbytes / ms / 1e6 / peak, 3)}
+s = slice(0, 200_000)
+ref = A[s].double() @ W1.double().t()
+out["err_vs_fp64"] = float((F.gemm_tf32x3(A[s].contiguous(), W1).double() - ref).abs().max() / ref.abs().max())
+out["err_cublas"] = float(((A[s] @ W1.t()).double() - ref).abs().max() / ref.abs().max())
+print(json.dumps(out))

@@ -41,7 +41,7 @@ def test_header_constants_match_python_mirror():
     assert int(defs["DMP_SEG_SIGN_BY_REV"]) == _lib.SEG_SIGN_BY_REV
     assert int(defs["DMP_SEG_NEGATE_OUT"]) == _lib.SEG_NEGATE_OUT
     assert int(defs["DMP_SEG_ONLY_FWD"]) == _lib.SEG_ONLY_FWD and int(defs["DMP_SEG_ONLY_REV"]) == _lib.SEG_ONLY_REV
-    assert int(defs["DMP_SEG_SPLIT_BY_REV"]) == _lib.SEG_SPLIT_BY_REV
+    assert int(defs["DMP_SEG_SPLIT_BY_REV"]) == _lib.SEG_SPLIT_BY_REV and int(defs["DMP_SEG_SHORT"]) == _lib.SEG_SHORT
     assert int(defs["DMP_EDGE_MIRRORED_HALVES"]) == _lib.EDGE_MIRRORED_HALVES
     assert int(defs["DMP_ORDER_SCM"]) == _lib.ORDER_SCM and int(defs["DMP_ORDER_UNC"]) == _lib.ORDER_UNC
     assert int(defs["DMP_EID_MASK"], 16) == _lib.EID_MASK

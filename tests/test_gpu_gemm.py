@@ -60,9 +60,7 @@ def test_gemm_epilogues(act, slope):
     torch.testing.assert_close(got, fn(plain + bias), rtol=1e-6, atol=1e-6)
     # row scale is applied to A as an individually rounded fp32 product
     got = F.gemm_tf32x3(A, Wt, row_scale=scale)
-    # (producer-side row scale runs on the interleaved-order kernel, the plain product on the cross-terms-first one:
-    # same value up to the accumulator's truncation pattern)
-    torch.testing.assert_close(got, F.gemm_tf32x3(scale.unsqueeze(1) * A, Wt), rtol=0, atol=2.5e-6 * float(got.abs().max()))
+    assert torch.equal(got, F.gemm_tf32x3(scale.unsqueeze(1) * A, Wt))
     # accumulate into an existing D
     D0 = torch.randn(M, N, device="cuda", generator=g)
     D = D0.clone()
@@ -142,32 +140,3 @@ def test_gemm_tn_column_sums(M, N):
     torch.testing.assert_close(sg.double(), G.double().sum(0), rtol=1e-6, atol=1e-6 * float(G.double().sum(0).abs().max()))
     ref = (c.double().unsqueeze(1) * X.double()).t() @ G.double()
     assert float((D.double() - ref).abs().max() / ref.abs().max()) <= 1e-5
-
-
-@pytest.mark.parametrize("N,K,M", [(128, 128, 70000), (64, 64, 33001), (128, 128, 97)])
-def test_gemm_acc_gather_epilogue(N, K, M):
-    """out += (c ⊙ A) Wt^T + sgn * norm * tab_{rev}[dst]: the gather term must be added exactly as fp32 ops."""
-    from dualmessagepassing_b200 import functional as F
-    g = torch.Generator(device="cuda").manual_seed(N + M)
-    nodes = 5000
-    A = torch.randn(M, K, device="cuda", generator=g)
-    Wt = torch.randn(N, K, device="cuda", generator=g) / 4
-    c = torch.rand(M, device="cuda", generator=g) * 6
-    norm = torch.rand(M, device="cuda", generator=g)
-    dst = torch.randint(0, nodes, (M,), device="cuda", generator=g, dtype=torch.int32)
-    rev = (torch.rand(M, device="cuda", generator=g) > 0.5).to(torch.uint8)
-    t0 = torch.randn(nodes, N, device="cuda", generator=g)
-    t1 = torch.randn(nodes, N, device="cuda", generator=g)
-    D0 = torch.randn(M, N, device="cuda", generator=g)
-    plain = F.gemm_tf32x3(A, Wt, row_scale=c)
-    D = D0.clone()
-    F.gemm_tf32x3_acc_gather(A, Wt, D, dst32=dst, tab_fwd=t0, tab_rev=t1, rev=rev, norm=norm, row_scale=c)
-    gathered = torch.where(rev.bool().unsqueeze(1), t1[dst.long()], t0[dst.long()]) * norm.unsqueeze(1)
-    want = (D0 + plain) + torch.where(rev.bool().unsqueeze(1), gathered, -gathered)
-    assert torch.equal(D, want)
-    # no flags / no norm: every edge is a forward edge (sign -1)
-    D = D0.clone()
-    F.gemm_tf32x3_acc_gather(A, Wt, D, dst32=dst, tab_fwd=t0)
-    # (the gather epilogue lives on the round-1 interleaved-order kernel, the plain product on the cross-terms-first one)
-    want = (D0 + F.gemm_tf32x3(A, Wt)) - t0[dst.long()]
-    torch.testing.assert_close(D, want, rtol=0, atol=2.5e-6 * float(want.abs().max()))

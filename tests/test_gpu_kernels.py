@@ -184,6 +184,21 @@ def test_million_edge_hub_sequential_bit_exact_and_two_level_close():
         assert float((seq[hub].double() - ref).abs().max()) <= 2e-6 * scale   # 1 M sequential fp32 adds drift further
 
 
+def test_short_segment_hint_is_bit_identical():
+    """DMP_SEG_SHORT (many segments of ~2 rows: the partitioned graph's a-/b-keyed reductions) only changes occupancy."""
+    from dualmessagepassing_b200 import _lib, functional as F
+    s, d, r = make_graph(seed=8, n=50_000, e0=60_000, rev="halves")
+    plan = _plan(s, d, 50_000, r)
+    G = torch.randn(len(s), 128, device="cuda")
+    for mode in (0, _lib.SEG_NEGATE_OUT):
+        a = F.segment_reduce(plan.b_indptr, plan.b_eid, G, 128, mode=mode)
+        b = F.segment_reduce(plan.b_indptr, plan.b_eid, G, 128, mode=mode | _lib.SEG_SHORT)
+        assert torch.equal(a, b)
+    cp = _cpu_plan(plan)
+    want = sc.seg_reduce(cp["a_indptr"], cp["a_eid"], G.cpu(), 128)
+    assert torch.equal(F.segment_reduce(plan.a_indptr, plan.a_eid, G, 128, mode=_lib.SEG_SHORT).cpu(), want)
+
+
 def test_strided_operands_use_leading_dimension():
     from dualmessagepassing_b200 import _lib, functional as F
     s, d, r = make_graph(seed=5, n=40, e0=200, rev="halves")
