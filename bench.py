@@ -549,6 +549,28 @@ def run_train(args, dev, world, rank, config, hbm_peak):
             "final_loss": float(loss.item())}
 
 
+def bind_to_local_numa(local_rank):
+    """Run this rank's host threads on the NUMA node its GPU hangs off, BEFORE the pinned staging buffers are allocated
+    (first-touch places them there): at N = 8 the e2e leg is bound by host memory / PCIe root-complex traffic, and a
+    staging buffer on the remote socket halves the copy rate.  Returns a description for the JSON line."""
+    try:
+        props = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bdf
+        node = int(open(base + "/numa_node").read())
+        cpus = open(base + "/local_cpulist").read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            lo, _, hi = part.partition("-")
+            ids.update(range(int(lo), int(hi or lo) + 1))
+        allowed = ids & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return {"gpu": bdf, "numa_node": node, "cpus": cpus, "bound": bool(allowed)}
+    except Exception as exc:
+        return {"bound": False, "why": "%s: %s" % (type(exc).__name__, str(exc)[:120])}
+
+
 def run_ours(args):
     import torch.distributed as dist
 
@@ -564,6 +586,7 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     _lib.load()  # fail loudly if the CUDA extension is missing
+    numa = bind_to_local_numa(local_rank) if world > 1 else None
 
     n, e0, h, desc = WORKLOADS[args.workload]
     E = 2 * e0
@@ -851,7 +874,7 @@ def run_ours(args):
                                 "(fp32-level accuracy: <= 1e-6 max-norm vs fp64 per product; cuBLAS sgemm 5e-7); sparse "
                                 "core in fp32"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
-            "clocks": clocks, "parity": parity, "multi_gpu_parity": mg_parity, "gpu_baseline": gpu_baseline,
+            "clocks": clocks, "host_numa_binding": numa, "parity": parity, "multi_gpu_parity": mg_parity, "gpu_baseline": gpu_baseline,
             "kernels": kernels, "mlp0": mlp0, "cfg4": cfg4, "train": train,
             "train_all": {k: v for k, v in train_all.items() if v is not train},
             "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9,

@@ -34,6 +34,7 @@ _vp, _i64, _i32, _f32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_
 # name -> argtypes; every entry must be exported by the library (tests/test_abi.py checks the header too)
 SIGNATURES = {
     "dmp_version": [],
+    "dmp_set_sm_reserve": [_i32],
     "dmp_plan_workspace_bytes": [_i64, _i64, ctypes.POINTER(ctypes.c_int64)],
     "dmp_plan_build": [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                        _vp, _vp, _vp, _vp, _i64, _vp],
@@ -113,6 +114,14 @@ def call(name, device, *args, tag=None, nbytes=None):
             rc = fn(*args)
     LAUNCHES += 1
     check(rc, name)
+
+
+# SMs left to an overlapped NCCL collective while it is in flight (parallel.py / fused.py); 0 disables
+SM_RESERVE = int(os.environ.get("DMP_SM_RESERVE", "16"))
+
+
+def sm_reserve(n):
+    check(load().dmp_set_sm_reserve(int(n)), "dmp_set_sm_reserve")
 
 
 def ptr(t):

@@ -13,6 +13,8 @@ constexpr int kThreads = 256;   // 8 warps per CTA everywhere
 constexpr int kNumSMs = 148;    // B200
 
 void set_error(const char* fmt, ...);
+// SMs the persistent (one-CTA-per-SM) tensor-core kernels may occupy: 148 minus dmp_set_sm_reserve()
+int persistent_sms();
 
 #define DMP_CHECK_ARG(cond, ...)            \
   do {                                      \

@@ -824,7 +824,7 @@ template <int NOUT, int K, int MODE>
 static int launch_v2_mode(const V2Params& p, cudaStream_t stream) {
   using L = V2Smem<K>;
   constexpr int kHalves = (MODE >= kV2DualStore) ? NOUT / 64 : 1;
-  const int64_t streams = kNumSMs / kHalves;
+  const int64_t streams = persistent_sms() / kHalves;
   V2Params q = p;
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));

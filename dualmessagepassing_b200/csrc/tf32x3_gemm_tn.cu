@@ -479,7 +479,8 @@ extern "C" int dmp_gemm_tn_tf32x3(const float* X, int64_t ldx, const float* row_
                            aligned_to(G, 16)),
                 "gemm_tn_tf32x3: operands must have dense 16-byte aligned rows");
   const int64_t stages = (E + kTnEdges - 1) / kTnEdges;
-  int64_t grid = stages < kNumSMs ? stages : kNumSMs;
+  const int sms = persistent_sms();
+  int64_t grid = stages < sms ? stages : sms;
   if (grid < 1) grid = 1;
   DMP_CHECK_ARG(workspace != nullptr && workspace_bytes >= grid * (M * N + M + N) * 4,
                 "gemm_tn_tf32x3: workspace too small");

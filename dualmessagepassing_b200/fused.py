@@ -276,10 +276,12 @@ class _FusedDMPLayer(torch.autograd.Function):
         # ranks' rows runs on NCCL's stream WHILE this rank aggregates its own edges (the node side needs no remote row)
         csc_indptr, X_v_full, gather_work = plan.csc_indptr, X_v, None
         if part is not None:
+            _lib.sm_reserve(0)     # (a previous call that raised between reserve and release must not leak its reserve)
             from .parallel import all_gather_rows_async
             n_lo, n_hi, group = part
             X_v_full, gather_work = all_gather_rows_async(X_v, group)
             csc_indptr = plan.csc_indptr[n_lo:n_hi + 1]
+            _lib.sm_reserve(_lib.SM_RESERVE)     # persistent kernels leave SMs to the collective while it is in flight
 
         # ---- node side (dmpnn.py:113-133): project, aggregate incident edge messages, self loop, bias
         in_t, out_t = in_w.t(), out_w.t()
@@ -335,6 +337,7 @@ class _FusedDMPLayer(torch.autograd.Function):
             S = _rowmm(X_e, eloop_w.t())
         if gather_work is not None:
             gather_work.wait()
+            _lib.sm_reserve(0)
         Qd = _rowmm(X_v_full, dst_w.t())
         Qs = _rowmm(X_v_full, src_w.t())
         edge_pre = edge_update(plan, S, P, Qd, Qs, ebias, order, out=S)
@@ -442,6 +445,7 @@ class _FusedDMPLayer(torch.autograd.Function):
                 partial = _rowmm(dQd, dst_w)
                 _rowmm(dQs, src_w, out=partial, accumulate=True)
                 dX_v, scatter_work = reduce_scatter_rows_async(partial, group)
+                _lib.sm_reserve(_lib.SM_RESERVE)
         if need_xe:
             if gather:
                 # 1. dX_e <- sgn*norm*(gN W_n^T)[dst]: streaming gather from node-sized tables (high-occupancy kernel:
@@ -502,6 +506,7 @@ class _FusedDMPLayer(torch.autograd.Function):
                 d_out = _tnmm(X_e, T[:, H:])
         if scatter_work is not None:
             scatter_work.wait()
+            _lib.sm_reserve(0)
             _rowmm(gN, nloop_w, out=dX_v, accumulate=True)
         if part is not None and need_w:
             # every weight gradient above is a partial sum over this rank's nodes/edges

@@ -79,6 +79,11 @@ extern "C" {
 
 DMP_API const char* dmp_last_error(void);
 DMP_API int dmp_version(void);
+/* The tensor-core kernels are persistent, one CTA per SM, with a static tile schedule: when another kernel (an NCCL
+ * collective overlapped with the layer, parallel.py) occupies some SMs, the CTAs that cannot become resident start late
+ * and stretch the launch to up to twice its time.  dmp_set_sm_reserve(n) (thread-local, default 0) makes the following
+ * launches of this thread use 148 - n CTAs, leaving n SMs to the collective. */
+DMP_API int dmp_set_sm_reserve(int sms);
 
 /* ------------------------------------------------------------------------------------------------
  * Graph plan (row A0): replaces DGL's COO->CSC conversion behind `fn.sum` (dmpnn.py:92,163),
