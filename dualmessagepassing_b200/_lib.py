@@ -117,7 +117,7 @@ def call(name, device, *args, tag=None, nbytes=None):
 
 
 # SMs left to an overlapped NCCL collective while it is in flight (parallel.py / fused.py); 0 disables
-SM_RESERVE = int(os.environ.get("DMP_SM_RESERVE", "16"))
+SM_RESERVE = int(os.environ.get("DMP_SM_RESERVE", "0"))
 
 
 def sm_reserve(n):

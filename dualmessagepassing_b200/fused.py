@@ -338,8 +338,12 @@ class _FusedDMPLayer(torch.autograd.Function):
         if gather_work is not None:
             gather_work.wait()
             _lib.sm_reserve(0)
-        Qd = _rowmm(X_v_full, dst_w.t())
-        Qs = _rowmm(X_v_full, src_w.t())
+        if DUAL_GEMM and _use_tc(X_v_full, dst_w.t()):
+            # both endpoint tables in ONE pass over X_v (same operand, two weights)
+            Qd, Qs = gemm_tf32x3_dual(X_v_full, dst_w.t().contiguous(), src_w.t().contiguous(), mode="separate")
+        else:
+            Qd = _rowmm(X_v_full, dst_w.t())
+            Qs = _rowmm(X_v_full, src_w.t())
         edge_pre = edge_update(plan, S, P, Qd, Qs, ebias, order, out=S)
         del P, Qd, Qs
 
@@ -451,8 +455,11 @@ class _FusedDMPLayer(torch.autograd.Function):
                 # 1. dX_e <- sgn*norm*(gN W_n^T)[dst]: streaming gather from node-sized tables (high-occupancy kernel:
                 #    a GEMM epilogue cannot keep enough random 128-byte loads in flight, measured 37 ms vs 7 ms here)
                 # 2. both projections of gE accumulate onto it in ONE pass (coef scales the second product's rows)
-                tab_in = _rowmm(gN, in_w)
-                tab_out = _rowmm(gN, out_w) if plan.rev is not None else None
+                if plan.rev is not None and DUAL_GEMM and _use_tc(gN, in_w):
+                    tab_in, tab_out = gemm_tf32x3_dual(gN, in_w, out_w, mode="separate")    # one pass over gN
+                else:
+                    tab_in = _rowmm(gN, in_w)
+                    tab_out = _rowmm(gN, out_w) if plan.rev is not None else None
                 dX_e = torch.empty((E, Din), dtype=gE.dtype, device=gE.device)
                 edge_backward(plan, ctx.norm_flat, tab_in, None, want_CG=False, T=dX_e, gN_rev=tab_out, row_offset=n_lo)
                 del tab_in, tab_out
