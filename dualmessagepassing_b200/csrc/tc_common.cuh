@@ -48,6 +48,16 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// One elected lane of a CONVERGED warp (elect.sync).  Issuing tcgen05.mma under `if (lane == 0)` makes ptxas wrap every
+// MMA in an ELECT / BRA.U.ANY loop (it needs the descriptors in uniform registers and cannot prove the branch is taken
+// by one lane only): ~12 extra dependent instructions per MMA in the single thread that is the critical path of the
+// projection kernels.  With elect.sync the region is known to be single-threaded.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{ .reg .pred p; elect.sync _|p, 0xffffffff; selp.u32 %0, 1, 0, p; }" : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");

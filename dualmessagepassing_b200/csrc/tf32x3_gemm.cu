@@ -60,7 +60,6 @@ struct V2Params {
   const float* W1; const float* W2; int64_t ldw;   // [N, K] (nn.Linear layout); W2 only in the dual forms
   const float* scale;                              // single/accumulate: D += s_r * acc_r; dual: c_r
   const float* pre_scale;                          // single, non-accumulate: rows of A are scaled first (rounded product)
-  int hi_slots, lo_slots;                          // 128-row kernel: split of the k-block slots between the hi and lo rings
   const float* bias;
   const float* aux; int64_t ld_aux;
   float* D; int64_t ldd;
@@ -252,7 +251,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) tf32x3_gemm_v2_kernel(const V2P
       mbar_wait(bar_acc_empty + 8 * acc, acc_phase ^ 1);
       mbar_wait(bar_full + 8 * stage, phase);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kV2Rows);
         const uint32_t a_hi = sA + stage * L::kStageBytes;
         const uint32_t a_lo = a_hi + L::kHalfBytes;
@@ -448,7 +447,7 @@ constexpr int kV3MaxLoSlots = 4;
 constexpr int kV3SlotBytes = kV3Rows * 128;         // 16 KB: 128 rows x 32 floats
 constexpr int kV3XchgBytes = 8 * 4096;              // dual: per epilogue warp 32 rows x 32 features
 // 224 KB of tiles either way: the dual forms give two hi slots to the epilogue's exchange buffer
-// (ring split = V2Params::hi_slots / lo_slots, 14 slots in all for the single forms, 12 for the dual ones)
+// (14 k-block slots in all for the single forms, 12 for the dual ones)
 constexpr int kV3SlotsSingle = 14, kV3SlotsDual = 12, kV3MaxHiSlots = 12;
 constexpr int kV3Smem = kV3SlotsSingle * kV3SlotBytes + 512 + 1024;
 static_assert(kV3SlotsDual * kV3SlotBytes + kV3XchgBytes == kV3SlotsSingle * kV3SlotBytes, "");
@@ -458,7 +457,11 @@ __global__ void __launch_bounds__(kV3Threads, 1) tf32x3_gemm_v3_kernel(const V2P
                                                                        const __grid_constant__ CUtensorMap tmap) {
   constexpr bool kDual = MODE >= kV2DualStore;
   constexpr int kKBlocks = K / kKB;                           // k-blocks per tile: 4 or 2
-  const int kV3HiSlots = p.hi_slots, kV3LoSlots = p.lo_slots;       // kernel-uniform ring sizes (host-validated)
+  // ring split: 2 lo slots (they only bridge split -> cross-term MMA retirement), everything else is TMA prefetch depth.
+  // COMPILE-TIME on purpose: as launch parameters (swept in profiles/r2_gemm_sweep.txt: 1 lo slot -12 %, 3-4 no gain) the
+  // run-time modulo in the single MMA-issuing thread cost 15-25 % of every projection
+  constexpr int kV3LoSlots = 2;
+  constexpr int kV3HiSlots = (kDual ? kV3SlotsDual : kV3SlotsSingle) - kV3LoSlots;
   constexpr int kHalves = kDual ? NOUT / 64 : 1;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -536,7 +539,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) tf32x3_gemm_v3_kernel(const V2P
 
   if (warp == kV3TmaWarp) {
     // =========================== TMA ISSUER ===========================
-    if (lane == 0) {
+    if (elect_one()) {   // (the warp arrives here converged)
       int slot = 0;
       uint32_t sphase = 0;
 #pragma unroll 1
@@ -604,7 +607,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) tf32x3_gemm_v3_kernel(const V2P
       for (int kb = 0; kb < kKBlocks; ++kb) {
         mbar_wait(bar_full_lo + 8 * ls, lphase);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t a_hi = sHi + ((hs0 + kb) % kV3HiSlots) * kV3SlotBytes;
           const uint32_t a_lo = sLo + ls * kV3SlotBytes;
 #pragma unroll
@@ -622,7 +625,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) tf32x3_gemm_v3_kernel(const V2P
         if (++ls == kV3LoSlots) { ls = 0; lphase ^= 1; }
       }
       // pass 2: the dominant hi*hi terms
-      if (lane == 0) {
+      if (elect_one()) {
 #pragma unroll
         for (int kb = 0; kb < kKBlocks; ++kb) {
           const uint32_t a_hi = sHi + ((hs0 + kb) % kV3HiSlots) * kV3SlotBytes;
@@ -842,13 +845,6 @@ static int launch_v2_mode(const V2Params& p, cudaStream_t stream) {
     const int64_t tiles = (p.M + kV3Rows - 1) / kV3Rows;
     const unsigned grid = (unsigned)((tiles < streams ? tiles : streams) * kHalves);
     q.use_tma = 1;
-    // ring split: lo slots only bridge split -> cross-term MMA retirement, everything else is TMA prefetch depth
-    // (DMP_V3_LO overrides for experiments: scripts/gemm_bench.py)
-    static const int lo_env = [] { const char* e = getenv("DMP_V3_LO"); return e ? atoi(e) : 0; }();
-    constexpr int kSlots = (MODE >= kV2DualStore) ? kV3SlotsDual : kV3SlotsSingle;
-    q.lo_slots = (lo_env >= 1 && lo_env <= kV3MaxLoSlots) ? lo_env : 2;
-    q.hi_slots = kSlots - q.lo_slots;
-    if (q.hi_slots > kV3MaxHiSlots) q.hi_slots = kV3MaxHiSlots;
     tf32x3_gemm_v3_kernel<NOUT, K, MODE><<<grid, kV3Threads, kV3Smem, stream>>>(q, tmap);
     return launch_status("tf32x3_gemm_v3_kernel");
   }

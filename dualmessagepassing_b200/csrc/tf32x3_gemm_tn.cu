@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(kTnThreads, 1) tf32x3_gemm_tn_kernel(const TnP
       for (; st < st_hi; ++st) {
         mbar_wait(bar_full + 8 * aslot, phase);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t g_hi = ghi + (uint32_t)shi * L::kGBytes, g_lo = glo + (uint32_t)slo * L::kGBytes;
           const uint32_t a_hi = tmem_base + kTnACol + (uint32_t)(aslot * kTnAColsPerSlot), a_lo = a_hi + kTnEdges;
 #pragma unroll

@@ -1,5 +1,6 @@
 """Projection kernels at config-5 size (E = 40 M rows, 128 x 128): CUDA-event time per launch, fraction of the measured HBM
-peak, error vs fp64 on a sample.  `DMP_V3_LO=n python scripts/gemm_bench.py` sweeps the hi/lo ring split."""
+peak, error vs fp64 on a sample.  (profiles/r2_gemm_sweep.txt was taken with a build whose hi/lo ring split was a launch
+parameter, DMP_V3_LO; the split is compile-time again: the run-time modulo slowed the MMA-issuing thread.)"""
 import json, os, sys, torch
 sys.path.insert(0, ".")
 from dualmessagepassing_b200 import functional as F
