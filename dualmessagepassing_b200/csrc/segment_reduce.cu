@@ -159,9 +159,8 @@ static int launch(const SegParams& p, cudaStream_t stream) {
     return DMP_ERR_UNSUPPORTED;
   }
   if constexpr (VEC == 4 && G == 32 && ITER == 1) {
-    if ((p.mode & DMP_SEG_SHORT) && !filter) {
-      if (p.mode & DMP_SEG_SPLIT_BY_REV) segment_reduce_kernel<VEC, G, ITER, 2, 2, 6><<<(unsigned)blocks, kThreads, 0, stream>>>(p);
-      else segment_reduce_kernel<VEC, G, ITER, 2, 0, 6><<<(unsigned)blocks, kThreads, 0, stream>>>(p);
+    if ((p.mode & DMP_SEG_SHORT) && !(p.mode & DMP_SEG_SPLIT_BY_REV) && !filter) {
+      segment_reduce_kernel<VEC, G, ITER, 2, 0, 6><<<(unsigned)blocks, kThreads, 0, stream>>>(p);
       return launch_status("segment_reduce_kernel<short>");
     }
   }

@@ -65,53 +65,6 @@ _ACT_NAME = {v: k for k, v in _ACT.items()}
 # below this many rows the persistent tcgen05 kernels' fixed cost (weight split per CTA, TMEM allocation, second
 # reduce launch) exceeds what cuBLAS sgemm needs for the whole product
 TC_MIN_ROWS = 16384
-# The segment reductions (HBM-bound, no shared memory, 40 registers in their DMP_SEG_SHORT form) are launched on a second
-# stream NEXT TO the tensor-core projections of the other side of the layer (which leave 35-55 % of the HBM bandwidth
-# idle): small enough to be co-resident with a 576-thread persistent CTA, they run in its shadow.  Only for graphs with at
-# least OVERLAP_MIN_EDGES edges (below that the fork/join costs more than the reduction).  DMP_OVERLAP=0 disables.
-OVERLAP = __import__("os").environ.get("DMP_OVERLAP", "1") != "0"
-OVERLAP_MIN_EDGES = 1 << 20
-_side_streams = {}
-
-
-def _side_stream(device):
-    key = (device.index if device.index is not None else torch.cuda.current_device())
-    st = _side_streams.get(key)
-    if st is None:
-        st = _side_streams[key] = torch.cuda.Stream(device=device)
-    return st
-
-
-class _Fork:
-    """`with _Fork(device, enabled) as f:` runs the body on the side stream after everything enqueued so far on the
-    current stream; `f.join(*tensors)` makes the current stream wait for it and hands the tensors over."""
-
-    def __init__(self, device, enabled):
-        self.enabled, self.device = enabled, device
-
-    def __enter__(self):
-        if self.enabled:
-            self.main = torch.cuda.current_stream(self.device)
-            self.side = _side_stream(self.device)
-            self.side.wait_stream(self.main)
-            self.ctx = torch.cuda.stream(self.side)
-            self.ctx.__enter__()
-        return self
-
-    def __exit__(self, *exc):
-        if self.enabled:
-            self.done = self.side.record_event()
-            self.ctx.__exit__(*exc)
-        return False
-
-    def join(self, *tensors):
-        if self.enabled:
-            self.main.wait_event(self.done)
-            for t in tensors:
-                if t is not None:
-                    t.record_stream(self.main)      # allocated on the side stream, consumed on this one
-
-
 # same-operand projection pairs in ONE launch (dmp_gemm_tf32x3_dual); False = two dmp_gemm_tf32x3 launches (A/B runs)
 DUAL_GEMM = __import__("os").environ.get("DMP_DUAL_GEMM", "1") != "0"
 
@@ -341,22 +294,16 @@ class _FusedDMPLayer(torch.autograd.Function):
         agg_first = _use_tc(X_e, in_t) and Din in (64, 128)
         A2 = None
         m_off = 0 if plan.rev_layout in ("none", "halves") else H   # column offset of the reversed branch in [E, 2H]
-        overlap = OVERLAP and agg_first and part is None and E >= OVERLAP_MIN_EDGES and not plan.long_chunk
-        fork = None
         if agg_first:
             split = plan.rev is not None
-            with _Fork(X_e.device, overlap) as fork:     # side stream: runs in the shadow of the edge-side projection below
-                A2 = segment_reduce(csc_indptr, plan.csc_eid, X_e, Din, plan=plan, w_perm=norm_perm,
-                                    mode=_lib.SEG_SIGN_BY_REV | (_lib.SEG_SPLIT_BY_REV if split else 0)
-                                    | (_lib.SEG_SHORT if overlap else 0), tag="segment_reduce.node_fwd")
-            if not overlap:
-                fork = None
-        if agg_first and fork is None:
+            A2 = segment_reduce(csc_indptr, plan.csc_eid, X_e, Din, plan=plan, w_perm=norm_perm,
+                                mode=_lib.SEG_SIGN_BY_REV | (_lib.SEG_SPLIT_BY_REV if split else 0),
+                                tag="segment_reduce.node_fwd")
             node_pre = _rowmm(X_v, nloop_w.t(), bias=nbias)
             _rowmm(A2[:, :Din], in_t, out=node_pre, accumulate=True)
             if split:
                 _rowmm(A2[:, Din:], out_t, out=node_pre, accumulate=True)
-        elif not agg_first:
+        else:
             Ln = _rowmm(X_v, nloop_w.t())
             if plan.rev_layout == "none":
                 M = _rowmm(X_e, in_t)
@@ -388,12 +335,6 @@ class _FusedDMPLayer(torch.autograd.Function):
         else:
             P = _rowmm(X_e, w_sd.t())
             S = _rowmm(X_e, eloop_w.t())
-        if fork is not None:      # the node side, now that the reduction that ran beside the projection has joined
-            fork.join(A2)
-            node_pre = _rowmm(X_v, nloop_w.t(), bias=nbias)
-            _rowmm(A2[:, :Din], in_t, out=node_pre, accumulate=True)
-            if split:
-                _rowmm(A2[:, Din:], out_t, out=node_pre, accumulate=True)
         if gather_work is not None:
             gather_work.wait()
             _lib.sm_reserve(0)
@@ -470,20 +411,17 @@ class _FusedDMPLayer(torch.autograd.Function):
             X_v_full = ctx.X_v_full
 
         # ---- sparse core backward: two sorted-segment sums of gE, one gather of gN ------
+        short = _lib.SEG_SHORT if E < 6 * plan.N else 0     # few rows per segment (partitioned graph): high-occupancy variant
+        dQd = segment_reduce(plan.a_indptr, plan.a_eid, gE, H, plan=plan, mode=short, tag="segment_reduce.dQd_bwd")
+        dQs = segment_reduce(plan.b_indptr, plan.b_eid, gE, H, plan=plan, mode=_lib.SEG_NEGATE_OUT | short,
+                             tag="segment_reduce.dQs_bwd")
         w_sd = src_w - dst_w
         Din = in_w.shape[0]
-        gather = (need_xe or need_w) and _use_tc(gE, w_sd) and Din in (64, 128)
-        overlap = OVERLAP and gather and need_xe and part is None and E >= OVERLAP_MIN_EDGES and not plan.long_chunk
-        # few rows per segment (partitioned graph), or launched beside a tensor-core kernel: the 40-register variant
-        short = _lib.SEG_SHORT if (E < 6 * plan.N or overlap) else 0
-        with _Fork(gE.device, overlap) as fork:      # side stream: in the shadow of the dX_e gather + dual projection below
-            dQd = segment_reduce(plan.a_indptr, plan.a_eid, gE, H, plan=plan, mode=short, tag="segment_reduce.dQd_bwd")
-            dQs = segment_reduce(plan.b_indptr, plan.b_eid, gE, H, plan=plan, mode=_lib.SEG_NEGATE_OUT | short,
-                                 tag="segment_reduce.dQs_bwd")
         # Gradient of the node aggregation w.r.t. the edge side.  On the tensor-core path nothing edge-sized is
         # materialised for it: dX_e receives  sgn*norm*(gN W_n^T)[dst]  from node-sized tables and dW_in / dW_out
         # come from the aggregate-first sums A2 saved by forward (a node-sized reduction each).  Otherwise
         # T = sgn*norm*gN[dst] is written out and fed to plain GEMMs.
+        gather = (need_xe or need_w) and _use_tc(gE, w_sd) and Din in (64, 128)
         T = None
         if not gather:
             m_cols = H + ctx.m_off
@@ -499,11 +437,7 @@ class _FusedDMPLayer(torch.autograd.Function):
         # ---- dense backward --------------------------------------------------------------------------------
         dX_v = dX_e = None
         scatter_work = None
-
-        def node_input_grad():
-            nonlocal dX_v, scatter_work
-            if not need_xv:
-                return
+        if need_xv:
             if part is None:
                 dX_v = _rowmm(gN, nloop_w)
                 _rowmm(dQd, dst_w, out=dX_v, accumulate=True)
@@ -516,9 +450,6 @@ class _FusedDMPLayer(torch.autograd.Function):
                 _rowmm(dQs, src_w, out=partial, accumulate=True)
                 dX_v, scatter_work = reduce_scatter_rows_async(partial, group)
                 _lib.sm_reserve(_lib.SM_RESERVE)
-
-        if not overlap:
-            node_input_grad()      # (partitioned: starts the reduce-scatter before the long edge-side work)
         if need_xe:
             if gather:
                 # 1. dX_e <- sgn*norm*(gN W_n^T)[dst]: streaming gather from node-sized tables (high-occupancy kernel:
@@ -549,9 +480,6 @@ class _FusedDMPLayer(torch.autograd.Function):
                 else:
                     _rowmm(T[:, :H], in_w, out=dX_e, accumulate=True)
                     _rowmm(T[:, H:], out_w, out=dX_e, accumulate=True)
-        if overlap:
-            fork.join(dQd, dQs)    # the two reductions ran beside the gather + dual projection above
-            node_input_grad()
         d_in = d_out = d_src = d_dst = d_nloop = d_eloop = d_nb = d_eb = None
         if need_w:
             d_nloop, _, d_nb = _tnmm(X_v, gN, colsum_g=True)

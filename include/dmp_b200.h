@@ -56,10 +56,8 @@ extern "C" {
                                    edge-sized projection by two node-sized ones. */
 
 #define DMP_SEG_SHORT 32 /* hint: segments hold only a few rows on average (destination-range partition: ~2.5 local edges
-                            per global segment): a higher-occupancy variant with fewer rows in flight per lane (40
-                            registers).  Same additions in the same order -- results are bit-identical with or without
-                            the hint.  Also the variant to launch on a second stream next to a tensor-core kernel: it
-                            is small enough to be co-resident with one (fused.py, OVERLAP). */
+                            per global segment): a higher-occupancy variant with fewer rows in flight per lane.  Same
+                            additions in the same order -- results are bit-identical with or without the hint. */
 
 /* dmp_edge_update order */
 #define DMP_ORDER_SCM 0 /* ((eloop + add) + agg) + ebias   dmpnn.py:147-149  */
