@@ -48,7 +48,10 @@ constexpr int kTnXWarps = 8, kTnFlushWarps = 4, kTnGWarps = 4;
 constexpr int kTnMmaWarp = kTnXWarps + kTnFlushWarps;     // 12
 constexpr int kTnGThreads = kTnGWarps * 32;
 constexpr int kTnThreads = (kTnXWarps + kTnFlushWarps + 1 + kTnGWarps) * 32;  // 544
-constexpr int kFlushStages = 16;        // 512 edges per tensor-core accumulation chain
+#ifndef DMP_TN_FLUSH_STAGES
+#define DMP_TN_FLUSH_STAGES 16
+#endif
+constexpr int kFlushStages = DMP_TN_FLUSH_STAGES;   // x 32 edges per tensor-core accumulation chain
 constexpr int kTnTmemCols = 512;
 
 struct TnParams {

@@ -17,6 +17,31 @@ import torch
 from .constants import EDGEID, EDGELABEL, REVFLAG
 
 
+class _EdgeFrame(dict):
+    """`edata` of a DMPGraph: a dict that forgets the graph's reversed-flag layout hint when a flag tensor is assigned,
+    replaced or removed by the caller (a hint that outlives its flags would mis-plan the graph)."""
+    _FLAG_KEYS = (REVFLAG, "is_rev")
+
+    def __init__(self, graph):
+        super().__init__()
+        self._graph = graph
+
+    def __setitem__(self, key, value):
+        if key in self._FLAG_KEYS and self.get(key) is not value:
+            self._graph.rev_layout_hint = None
+        super().__setitem__(key, value)
+
+    def __delitem__(self, key):
+        if key in self._FLAG_KEYS:
+            self._graph.rev_layout_hint = None
+        super().__delitem__(key)
+
+    def pop(self, key, *default):
+        if key in self._FLAG_KEYS:
+            self._graph.rev_layout_hint = None
+        return super().pop(key, *default)
+
+
 class DMPGraph:
     def __init__(self, src, dst, num_nodes, device=None):
         src = torch.as_tensor(src, dtype=torch.int64, device=device)
@@ -26,11 +51,11 @@ class DMPGraph:
         self._src, self._dst = src, dst
         self._n = int(num_nodes)
         self.ndata = {}
-        self.edata = {}
+        self.rev_layout_hint = None  # "halves" when add_reversed_edges built the edge list; reset by _EdgeFrame
+        self.edata = _EdgeFrame(self)
         self._batch_num_nodes = None
         self._batch_num_edges = None
         self._dmp_plans = {}      # plan cache, see plan.get_plan
-        self.rev_layout_hint = None  # "halves" when add_reversed_edges built the edge list
 
     # ---- structure (DGL-compatible spellings) ------------------------------------------------------
     @property
@@ -105,7 +130,8 @@ class DMPGraph:
         g = DMPGraph(self._src.to(device, non_blocking=non_blocking),
                      self._dst.to(device, non_blocking=non_blocking), self._n)
         g.ndata = {k: v.to(device, non_blocking=non_blocking) for k, v in self.ndata.items()}
-        g.edata = {k: v.to(device, non_blocking=non_blocking) for k, v in self.edata.items()}
+        for k, v in self.edata.items():
+            g.edata[k] = v.to(device, non_blocking=non_blocking)
         if self._batch_num_nodes is not None:
             g._batch_num_nodes = self._batch_num_nodes.to(device)
             g._batch_num_edges = self._batch_num_edges.to(device)

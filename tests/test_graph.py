@@ -73,3 +73,19 @@ def test_build_graph_from_triplets_matches_oracle_and_golden():
     os_, od, orel, onorm = go.build_graph_from_triplets(n, R, case["triplets"].numpy())
     assert np.array_equal(os_, s.numpy()) and np.array_equal(orel, case["rel"].numpy())
     assert np.array_equal(onorm, case["norm"].numpy())
+
+
+def test_layout_hint_is_dropped_when_the_flags_are_replaced():
+    """a `rev_layout_hint` must not outlive the flag tensor it described."""
+    import dualmessagepassing_b200 as dmp
+    from dualmessagepassing_b200.constants import REVFLAG
+    g = dmp.add_reversed_edges(dmp.DMPGraph([0, 1, 2], [1, 2, 0], 3))
+    assert g.rev_layout_hint == "halves"
+    same = g.edata[REVFLAG]
+    g.edata[REVFLAG] = same                       # re-binding the same tensor keeps the hint
+    assert g.rev_layout_hint == "halves"
+    g.edata[REVFLAG] = torch.tensor([1, 0, 1, 0, 1, 0], dtype=torch.bool)
+    assert g.rev_layout_hint is None
+    g.rev_layout_hint = "general"
+    g.edata.pop(REVFLAG)
+    assert g.rev_layout_hint is None
