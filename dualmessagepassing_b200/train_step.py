@@ -16,7 +16,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from .constants import EDGELABEL, NODELABEL, OUTDEGREE, REVFLAG
+from .constants import EDGELABEL, NODELABEL, REVFLAG
 from .functional import segment_reduce
 from .graph import DMPGraph
 from .models import DMPNNRepNet

@@ -286,3 +286,59 @@ def test_fused_layer_equals_composed_path(mlp, act, rev):
             assert torch.equal(x, y), k
         else:
             torch.testing.assert_close(x, y, rtol=2e-5, atol=2e-5 * max(1.0, float(y.abs().max())), msg=lambda m: k + m)
+
+
+@pytest.mark.parametrize("mlp,bn,act", [(3, False, "tanh"), (3, True, "tanh"), (1, False, "relu"), (2, True, "sigmoid")])
+def test_fused_layer_covers_every_mlp_shape(mlp, bn, act):
+    """dmpnn.py:45-52 builds Linear [BN] act ... Linear for any depth; the whole-layer function must take all of them
+    (batch_norm=True, num_mlp_layers=1 used to fall back to torch.mm) and agree with the composed path."""
+    import copy
+    from dualmessagepassing_b200 import _lib
+    s, d, r = make_graph(seed=41, n=600, e0=4000, rev="halves")
+    torch.manual_seed(6)
+    layer = dmp.DMPLayer(64, 64, num_mlp_layers=mlp, batch_norm=bn, act_func=act).cuda().train()
+    ref = copy.deepcopy(layer)
+    ref.fused = False
+    g = dmp.DMPGraph(s, d, 600, device="cuda")
+    g.edata[REVFLAG] = torch.from_numpy(r).cuda()
+    xv, xe = torch.randn(600, 64, device="cuda"), torch.randn(len(s), 64, device="cuda")
+    gv, ge = torch.randn(600, 64, device="cuda"), torch.randn(len(s), 64, device="cuda")
+    outs = []
+    for mod in (layer, ref):
+        a, b = xv.clone().requires_grad_(True), xe.clone().requires_grad_(True)
+        _lib.PROFILE = []
+        nv, ne = mod(g, a, b)
+        torch.autograd.backward((nv, ne), (gv, ge))
+        tags, _lib.PROFILE = {t[0] for t in _lib.PROFILE}, None
+        outs.append(([nv.detach(), ne.detach(), a.grad, b.grad] + [p.grad for p in mod.parameters()], tags))
+    assert any(t.startswith("gemm_tf32x3") for t in outs[0][1]) and not any(t.startswith("gemm") for t in outs[1][1])
+    if bn:
+        assert {"bn_stats", "bn_act", "bn_backward"} <= outs[0][1]
+    names = ["node_out", "edge_out", "dXv", "dXe"] + [k for k, _ in layer.named_parameters()]
+    for k, x, y in zip(names, outs[0][0], outs[1][0]):
+        if act == "relu" and k not in ("node_out", "edge_out"):
+            continue   # act' flips (see the fp64 test)
+        if bn and k.endswith("bias") and float(y.abs().max()) < 1e-3:
+            # a bias in front of BatchNorm: its gradient is 0 in exact arithmetic, rounding noise on both paths
+            assert float(x.abs().max()) < 1e-3, k
+            continue
+        torch.testing.assert_close(x, y, rtol=3e-5, atol=3e-5 * max(1.0, float(y.abs().max())), msg=lambda m: k + " " + m)
+
+
+def test_active_dropout_runs_on_the_fused_path():
+    """dmpnn.py:138,154: drop(out) on the layer outputs -- applied on top of the fused function, not a reason to leave it."""
+    from dualmessagepassing_b200 import _lib
+    s, d, r = make_graph(seed=42, n=300, e0=2000, rev="halves")
+    layer = dmp.DMPLayer(64, 64, num_mlp_layers=2, batch_norm=False, act_func="relu", dropout=0.5).cuda().train()
+    g = dmp.DMPGraph(s, d, 300, device="cuda")
+    g.edata[REVFLAG] = torch.from_numpy(r).cuda()
+    xv, xe = torch.randn(300, 64, device="cuda"), torch.randn(len(s), 64, device="cuda")
+    _lib.PROFILE = []
+    nv, ne = layer(g, xv, xe)
+    tags, _lib.PROFILE = {t[0] for t in _lib.PROFILE}, None
+    assert any(t.startswith("gemm_tf32x3") for t in tags)
+    zeros = float((ne == 0).float().mean())
+    assert 0.4 < zeros < 0.6
+    layer.eval()
+    nv2, ne2 = layer(g, xv, xe)
+    assert float((ne2 == 0).float().mean()) < 0.1
