@@ -28,6 +28,7 @@
 // (round-to-nearest adds, L2-resident), and a second kernel adds the per-CTA partials in a fixed order ->
 // deterministic, no atomics.
 #include <stdlib.h>
+#include <type_traits>
 
 #include "tc_common.cuh"
 
@@ -44,10 +45,10 @@ constexpr int kTnXRaw = kTnXDepth + 1;                    // per-warp ring of ra
 constexpr int kTnASlots = 4;            // TMEM ring of X^T: 32 hi + 32 lo columns per stage
 constexpr int kTnAColsPerSlot = 2 * kTnEdges;
 constexpr int kTnACol = 256;            // first TMEM column of that ring (accumulators: columns [0, 2N))
-constexpr int kTnXWarps = 8, kTnFlushWarps = 4, kTnGWarps = 4;
+constexpr int kTnXWarps = 8, kTnFlushWarps = 4, kTnGWarps = 8;
 constexpr int kTnMmaWarp = kTnXWarps + kTnFlushWarps;     // 12
 constexpr int kTnGThreads = kTnGWarps * 32;
-constexpr int kTnThreads = (kTnXWarps + kTnFlushWarps + 1 + kTnGWarps) * 32;  // 544
+constexpr int kTnThreads = (kTnXWarps + kTnFlushWarps + 1 + kTnGWarps) * 32;  // 672
 // Stages (x 32 edges) per tensor-core accumulation chain.  The accumulator TRUNCATES, so the error of a chain grows
 // linearly with its length; measured on 4 M x 128 x 128 (max-norm vs fp64; cuBLAS sgemm 2.5e-6 .. 2.9e-6), 40 M-edge time:
 //   64 stages 1.6e-5, 7.99 ms | 32: 7.2e-6, 7.90 ms | 16 (round 1): 3.8e-6, 8.35 ms | 8: 1.9e-6, 8.67 ms
@@ -112,14 +113,19 @@ __global__ void __launch_bounds__(kTnThreads, 1) tf32x3_gemm_tn_kernel(const TnP
   const uint32_t bar_acc_full = sBar + 16 * kTnASlots, bar_acc_empty = bar_acc_full + 16;
   const uint32_t tmem_slot = bar_acc_empty + 16;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-  float* sum_scratch = reinterpret_cast<float*>(smem_raw + (sBar + 256 - smem_u32(smem_raw)));   // [4 warps][128]
+  float* sum_scratch = reinterpret_cast<float*>(smem_raw + (sBar + 256 - smem_u32(smem_raw)));   // [G warps + 1][128]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int kXActive = M / 32;       // lane quadrants that hold real features (2 for M = 64)
   const int xq = warp & 3, xh = warp >> 2;   // X producers: quadrant and stage parity
 
   // this CTA's contiguous range of 16-edge stages
   const int64_t stages_total = (p.E + kTnEdges - 1) / kTnEdges;
-  const bool interleave = (p.ablate & 32) == 0;   // stage s of CTA b = b + s * grid: neighbouring SMs stream neighbouring rows
+#ifdef DMP_DEBUG
+  const int ablate = p.ablate;
+#else
+  constexpr int ablate = 0;     // the ablation switches cost predicates and address recomputation in every inner loop
+#endif
+  const bool interleave = (ablate & 32) == 0;   // stage s of CTA b = b + s * grid: neighbouring SMs stream neighbouring rows
   const int64_t s_begin = interleave ? blockIdx.x : stages_total * blockIdx.x / gridDim.x;
   const int64_t s_end = stages_total * (blockIdx.x + 1) / gridDim.x;
   const int64_t s_step = interleave ? gridDim.x : 1;
@@ -175,7 +181,7 @@ __global__ void __launch_bounds__(kTnThreads, 1) tf32x3_gemm_tn_kernel(const TnP
     auto issue = [&](int64_t st) {
       const int64_t e0 = (s_begin + st * s_step) * kTnEdges;
       const uint32_t dst = xraw + (uint32_t)islot * L::kXBlockBytes + (uint32_t)(crow * 128 + cch * 16);
-      if (!(p.ablate & (4 | 64))) {
+      if (!(ablate & (4 | 64))) {
         if (e0 + kTnEdges <= p.E) {
 #pragma unroll
           for (int i = 0; i < kTnEdges / 4; ++i) cp_async16(dst + i * 512, xsrc + 4 * i * p.ldx, 16u);
@@ -209,20 +215,27 @@ __global__ void __launch_bounds__(kTnThreads, 1) tf32x3_gemm_tn_kernel(const TnP
       tc_fence_after();
       const uint32_t src = xraw + (uint32_t)rslot * L::kXBlockBytes + (uint32_t)lane * 4;
       const uint32_t t_slot = t_lane + aslot * kTnAColsPerSlot;
+      // warp-uniform choice made once per stage, not per element
+      auto split_stage = [&](auto with_scale) {
 #pragma unroll
-      for (int h16 = 0; h16 < kTnEdges / 16; ++h16) {
-        float hi[16], lo[16];
+        for (int h16 = 0; h16 < kTnEdges / 16; ++h16) {
+          float hi[16], lo[16];
 #pragma unroll
-        for (int r = 0; r < 16; ++r) {
-          float v = (p.ablate & 8) ? 0.0f : lds32(src + (h16 * 16 + r) * 128);
-          if constexpr (SX) sum_x = __fadd_rn(sum_x, v);
-          if (scaled) v = __fmul_rn(__shfl_sync(0xffffffffu, my_scale, h16 * 16 + r), v);
-          hi[r] = tf32_rna(v);
-          lo[r] = __fsub_rn(v, hi[r]);
+          for (int r = 0; r < 16; ++r) {
+            float v = (ablate & 8) ? 0.0f : lds32(src + (h16 * 16 + r) * 128);
+            if constexpr (SX) sum_x = __fadd_rn(sum_x, v);
+            if constexpr (decltype(with_scale)::value) v = __fmul_rn(__shfl_sync(0xffffffffu, my_scale, h16 * 16 + r), v);
+            // the tensor core reads only the top 19 bits of a tf32 operand (TMEM as well as smem), so the raw word IS
+            // the truncated hi part and lo = v - trunc(v) is exact: 2 instructions per element where cvt.rna.tf32
+            // expands to 6 (the X warps were 65 % busy with the rounding form)
+            hi[r] = v;
+            lo[r] = tf32_trunc_residual(v);
+          }
+          tmem_st16(t_slot + h16 * 16, hi);
+          tmem_st16(t_slot + kTnEdges + h16 * 16, lo);
         }
-        tmem_st16(t_slot + h16 * 16, hi);
-        tmem_st16(t_slot + kTnEdges + h16 * 16, lo);
-      }
+      };
+      if (scaled) split_stage(std::true_type{}); else split_stage(std::false_type{});
       if (++rslot == kTnXRaw) rslot = 0;
       if (st + 2 * kTnXDepth < n_stages) issue(st + 2 * kTnXDepth);   // overlaps the tcgen05.st latency
       cp_async_commit();
@@ -242,9 +255,9 @@ __global__ void __launch_bounds__(kTnThreads, 1) tf32x3_gemm_tn_kernel(const TnP
     }
   } else if (warp > kTnMmaWarp) {
     // =========================== G PRODUCERS: global -> swizzled hi tile, lo = g - trunc(g) ===========================
-    const int gt = threadIdx.x - (kTnMmaWarp + 1) * 32;   // 0..127
+    const int gt = threadIdx.x - (kTnMmaWarp + 1) * 32;   // 0..kTnGThreads-1
     constexpr int kGChunks = kTnEdges * N / 4;
-    constexpr int kGPer = kGChunks / kTnGThreads;          // 4 (or 2)
+    constexpr int kGPer = kGChunks / kTnGThreads;          // 4 (N = 128) or 2
     // bias gradients for free: a thread always handles the same 4 columns (128 % (N/4) == 0), so it keeps running
     // column sums of everything it streams; rows past E are zero-filled and add nothing
     float4 sum_g = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -254,14 +267,14 @@ __global__ void __launch_bounds__(kTnThreads, 1) tf32x3_gemm_tn_kernel(const TnP
     const uint32_t ghi = base + L::kGHiOff, glo = base + L::kGLoOff;
     int ihi = 0;
     // chunk i of this thread is row grow + (512 / N) i, column chunk gch: constant smem and global strides
-    constexpr int kRowStep = kTnGThreads / (N / 4);          // 4 (N = 128) or 8 (N = 64)
+    constexpr int kRowStep = kTnGThreads / (N / 4);          // 8 (N = 128) or 16 (N = 64)
     const int grow = gt / (N / 4), gch = gt % (N / 4);
     const float* gsrc = p.G + (s_begin * kTnEdges + grow) * p.ldg + gch * 4;
     const int64_t gadv = s_step * kTnEdges * p.ldg;
     auto issue = [&](int64_t st) {
       const int64_t e0 = (s_begin + st * s_step) * kTnEdges;
       const uint32_t g_hi = ghi + (uint32_t)ihi * L::kGBytes;
-      if (!(p.ablate & (4 | 128))) {
+      if (!(ablate & (4 | 128))) {
         if (e0 + kTnEdges <= p.E) {
 #pragma unroll
           for (int i = 0; i < kGPer; ++i) cp_async16(g_hi + offg[i], gsrc + kRowStep * i * p.ldg, 16u);
@@ -289,19 +302,23 @@ __global__ void __launch_bounds__(kTnThreads, 1) tf32x3_gemm_tn_kernel(const TnP
       // st - kTnLoStages: one wait covers the split's output buffer and the next copy's landing buffer
       if (st >= kTnLoStages) mbar_wait(bar_done + 8 * dslot, dphase);
       const uint32_t g_hi = ghi + (uint32_t)shi * L::kGBytes, g_lo = glo + (uint32_t)slo * L::kGBytes;
-      if (!(p.ablate & 8)) {
+      if (!(ablate & 8)) {
+        // all loads first: ptxas otherwise chains lds -> residual -> sts one chunk at a time (the profile showed the
+        // G warps 100 % busy, a third of it waiting for one LDS after the other, and everyone else waiting for them)
+        float4 v[kGPer];
+#pragma unroll
+        for (int i = 0; i < kGPer; ++i) v[i] = lds128(g_hi + offg[i]);
 #pragma unroll
         for (int i = 0; i < kGPer; ++i) {
-          const float4 v = lds128(g_hi + offg[i]);
           if constexpr (SG) {
-            sum_g.x = __fadd_rn(sum_g.x, v.x); sum_g.y = __fadd_rn(sum_g.y, v.y);
-            sum_g.z = __fadd_rn(sum_g.z, v.z); sum_g.w = __fadd_rn(sum_g.w, v.w);
+            sum_g.x = __fadd_rn(sum_g.x, v[i].x); sum_g.y = __fadd_rn(sum_g.y, v[i].y);
+            sum_g.z = __fadd_rn(sum_g.z, v[i].z); sum_g.w = __fadd_rn(sum_g.w, v[i].w);
           }
-          sts128(g_lo + offg[i], make_float4(tf32_trunc_residual(v.x), tf32_trunc_residual(v.y),
-                                             tf32_trunc_residual(v.z), tf32_trunc_residual(v.w)));
+          sts128(g_lo + offg[i], make_float4(tf32_trunc_residual(v[i].x), tf32_trunc_residual(v[i].y),
+                                             tf32_trunc_residual(v[i].z), tf32_trunc_residual(v[i].w)));
         }
       }
-      if (!(p.ablate & 1)) fence_proxy_async();
+      if (!(ablate & 1)) fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_full + 8 * fslot);
       if (++shi == kTnHiStages) shi = 0;
@@ -351,7 +368,7 @@ __global__ void __launch_bounds__(kTnThreads, 1) tf32x3_gemm_tn_kernel(const TnP
           const uint32_t a_hi = tmem_base + kTnACol + (uint32_t)(aslot * kTnAColsPerSlot), a_lo = a_hi + kTnEdges;
 #pragma unroll
           for (int j = 0; j < kTnEdges / 8; ++j) {
-            if (p.ablate & 2) break;
+            if (ablate & 2) break;
             const uint64_t dgh = smem_desc_mn32(g_hi + j * p.kadv, p.lbo, p.sbo, p.ltype);
             const uint64_t dgl = smem_desc_mn32(g_lo + j * p.kadv, p.lbo, p.sbo, p.ltype);
             // small terms first, the dominant hi*hi product last
@@ -386,7 +403,7 @@ __global__ void __launch_bounds__(kTnThreads, 1) tf32x3_gemm_tn_kernel(const TnP
       for (int c0 = 0; c0 < N; c0 += 32) {
         float v[32];
         tmem_ld32(t_lane + c0, v);
-        if (m < M && !(p.ablate & 16)) {
+        if (m < M && !(ablate & 16)) {
           float* q = part + (int64_t)c0 * M;
           if (f != 0) {      // all 32 reads in flight before the first add (L2 latency once, not 32 times)
             float old[32];
