@@ -405,15 +405,16 @@ __global__ void __launch_bounds__(kTnThreads, 1) tf32x3_gemm_tn_kernel(const TnP
         tmem_ld32(t_lane + c0, v);
         if (m < M && !(ablate & 16)) {
           float* q = part + (int64_t)c0 * M;
-          if (f != 0) {      // all 32 reads in flight before the first add (L2 latency once, not 32 times)
-            float old[32];
+          // Each element of the partial is only ever touched by this thread, so a fire-and-forget fp32 reduction at L2
+          // (round-to-nearest, program order per address) gives the same sum as load + add + store for half the L2
+          // traffic and no round trip -- the read-modify-write form cost 0.9 of this kernel's 8.5 ms.
+          if (f != 0) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) old[j] = __ldcg(q + j * M);
+            for (int j = 0; j < 32; ++j) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(q + j * M), "f"(v[j]) : "memory");
+          } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __fadd_rn(old[j], v[j]);
+            for (int j = 0; j < 32; ++j) q[j * M] = v[j];
           }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) q[j * M] = v[j];
         }
       }
       tc_fence_before();
