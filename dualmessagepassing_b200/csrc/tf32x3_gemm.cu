@@ -222,16 +222,19 @@ __global__ void __launch_bounds__(kV2Threads, 1) tf32x3_gemm_v2_kernel(const V2P
       }
 #pragma unroll
       for (int kb = 0; kb < kKBlocks; ++kb) {
+        float4 v[2];                         // loads before stores: the volatile asm keeps program order
+#pragma unroll
+        for (int i = 0; i < 2; ++i) v[i] = lds128(hi + kb * L::kBlockBytes + offs[i]);
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-          float4 v = lds128(hi + kb * L::kBlockBytes + offs[i]);
           if (p.pre_scale != nullptr) {      // (row_scale ⊙ A) as an individually rounded fp32 product, then the split
-            v.x = __fmul_rn(sc[i], v.x); v.y = __fmul_rn(sc[i], v.y); v.z = __fmul_rn(sc[i], v.z); v.w = __fmul_rn(sc[i], v.w);
-            sts128(hi + kb * L::kBlockBytes + offs[i], v);
+            v[i].x = __fmul_rn(sc[i], v[i].x); v[i].y = __fmul_rn(sc[i], v[i].y);
+            v[i].z = __fmul_rn(sc[i], v[i].z); v[i].w = __fmul_rn(sc[i], v[i].w);
+            sts128(hi + kb * L::kBlockBytes + offs[i], v[i]);
           }
           sts128(lo + kb * L::kBlockBytes + offs[i],
-                 make_float4(tf32_trunc_residual(v.x), tf32_trunc_residual(v.y), tf32_trunc_residual(v.z),
-                             tf32_trunc_residual(v.w)));
+                 make_float4(tf32_trunc_residual(v[i].x), tf32_trunc_residual(v[i].y), tf32_trunc_residual(v[i].z),
+                             tf32_trunc_residual(v[i].w)));
         }
       }
       fence_proxy_async();
@@ -575,16 +578,23 @@ __global__ void __launch_bounds__(kV3Threads, 1) tf32x3_gemm_v3_kernel(const V2P
 #pragma unroll
         for (int i = 0; i < 4; ++i) sc[i] = (r0 + 32 * i < p.M) ? __ldg(p.pre_scale + r0 + 32 * i) : 1.0f;
       }
+      // all four loads first (the volatile asm keeps program order: interleaved with the stores the chain is
+      // LDS -> residual -> STS four times over, and the MMA issuer waits for exactly this warp group k-block by k-block)
+      float4 v[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float4 v = lds128(hi + offs[i]);
-        if (p.pre_scale != nullptr) {        // (row_scale ⊙ A) as an individually rounded fp32 product, then the split
-          v.x = __fmul_rn(sc[i], v.x); v.y = __fmul_rn(sc[i], v.y); v.z = __fmul_rn(sc[i], v.z); v.w = __fmul_rn(sc[i], v.w);
-          sts128(hi + offs[i], v);
+      for (int i = 0; i < 4; ++i) v[i] = lds128(hi + offs[i]);
+      if (p.pre_scale != nullptr) {          // (row_scale ⊙ A) as an individually rounded fp32 product, then the split
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          v[i].x = __fmul_rn(sc[i], v[i].x); v[i].y = __fmul_rn(sc[i], v[i].y);
+          v[i].z = __fmul_rn(sc[i], v[i].z); v[i].w = __fmul_rn(sc[i], v[i].w);
+          sts128(hi + offs[i], v[i]);
         }
-        sts128(lo + offs[i], make_float4(tf32_trunc_residual(v.x), tf32_trunc_residual(v.y), tf32_trunc_residual(v.z),
-                                         tf32_trunc_residual(v.w)));
       }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        sts128(lo + offs[i], make_float4(tf32_trunc_residual(v[i].x), tf32_trunc_residual(v[i].y),
+                                         tf32_trunc_residual(v[i].z), tf32_trunc_residual(v[i].w)));
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_full_lo + 8 * ls);
