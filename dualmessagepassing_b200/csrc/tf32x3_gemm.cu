@@ -437,8 +437,8 @@ __global__ void __launch_bounds__(kV2Threads, 1) tf32x3_gemm_v2_kernel(const V2P
 // M = 128 costs 64 cycles at N = 128 (2048 MAC/clk/SM, the pipe's full rate) but 45 cycles at N = 64 (an issue floor),
 // so the 64-row tiles above pay 1.4x the tensor time per row.  Here N = 128, and cross-terms-first needs the whole K of
 // a 128-row tile resident: 64 KB of raw (= hi) data per tile, so hi and lo live in SEPARATE rings of k-block slots:
-//   hi ring  8 slots x 16 KB (two tiles at K = 128): TMA lands here; a tile's slots are held until its hi*hi pass retires
-//   lo ring  4 slots x 16 KB: written by the producer warps, released k-block by k-block as the cross-term pass retires
+//   hi ring  12 slots x 16 KB (three tiles at K = 128): TMA lands here; a tile's slots are held until its hi*hi pass retires
+//   lo ring   2 slots x 16 KB: written by the producer warps, released k-block by k-block as the cross-term pass retires
 // Warps: 0-7 epilogue, 8 MMA issuer, 9-16 lo producers, 17 TMA issuer (decoupled from the producers so that the loads of
 // tile t+2 start the moment tile t retires).  MMA order per tile: for every k-block [lo*hi, hi*lo] x 4 k-steps (commit
 // frees the lo slot), then for every k-block hi*hi x 4 (one commit frees the tile's hi slots and publishes the
@@ -448,12 +448,12 @@ constexpr int kV3Threads = 18 * 32;
 constexpr int kV3TmaWarp = 17;
 constexpr int kV3MaxLoSlots = 4;
 constexpr int kV3SlotBytes = kV3Rows * 128;         // 16 KB: 128 rows x 32 floats
-constexpr int kV3XchgBytes = 8 * 4096;              // dual: per epilogue warp 32 rows x 32 features
-// 224 KB of tiles either way: the dual forms give two hi slots to the epilogue's exchange buffer
-// (14 k-block slots in all for the single forms, 12 for the dual ones)
-constexpr int kV3SlotsSingle = 14, kV3SlotsDual = 12, kV3MaxHiSlots = 12;
-constexpr int kV3Smem = kV3SlotsSingle * kV3SlotBytes + 512 + 1024;
-static_assert(kV3SlotsDual * kV3SlotBytes + kV3XchgBytes == kV3SlotsSingle * kV3SlotBytes, "");
+// 224 KB of k-block slots (14) for every form.  The dual forms interleave the two weight matrices lane by lane
+// (TMEM lane 2i = row f0+i of W1, lane 2i+1 = the same row of W2), so the two accumulators of a feature sit in
+// NEIGHBOURING LANES OF ONE WARP and the epilogue combines them with shuffles -- the earlier layout (lanes 0..63 / 64..127)
+// put them in different warps and cost a 32 KB exchange buffer, two named barriers and 64 KB of shared-memory traffic per tile.
+constexpr int kV3Slots = 14, kV3MaxHiSlots = 12;
+constexpr int kV3Smem = kV3Slots * kV3SlotBytes + 512 + 1024;
 
 template <int NOUT, int K, int MODE>
 __global__ void __launch_bounds__(kV3Threads, 1) tf32x3_gemm_v3_kernel(const V2Params p,
@@ -464,14 +464,13 @@ __global__ void __launch_bounds__(kV3Threads, 1) tf32x3_gemm_v3_kernel(const V2P
   // COMPILE-TIME on purpose: as launch parameters (swept in profiles/r2_gemm_sweep.txt: 1 lo slot -12 %, 3-4 no gain) the
   // run-time modulo in the single MMA-issuing thread cost 15-25 % of every projection
   constexpr int kV3LoSlots = 2;
-  constexpr int kV3HiSlots = (kDual ? kV3SlotsDual : kV3SlotsSingle) - kV3LoSlots;
+  constexpr int kV3HiSlots = kV3Slots - kV3LoSlots;
   constexpr int kHalves = kDual ? NOUT / 64 : 1;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sHi = base;
   const uint32_t sLo = sHi + kV3HiSlots * kV3SlotBytes;
-  const uint32_t sX = sLo + kV3LoSlots * kV3SlotBytes;
-  const uint32_t sBar = sX + (kDual ? kV3XchgBytes : 0);      // both forms: 224 KB of tiles (+ exchange) below the barriers
+  const uint32_t sBar = sLo + kV3LoSlots * kV3SlotBytes;      // 224 KB of tiles below the barriers
   const uint32_t bar_raw = sBar;                              // 12: TMA completion of a hi slot
   const uint32_t bar_empty_hi = sBar + 96;                    // 12: the tile that used the hi slot has retired
   const uint32_t bar_full_lo = sBar + 192;                    // <= 4: lo slot written
@@ -515,7 +514,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) tf32x3_gemm_v3_kernel(const V2P
   if (warp < 4) {
     const int l = warp * 32 + lane;
     const float* wrow;
-    if constexpr (kDual) wrow = ((l < 64) ? p.W1 : p.W2) + (int64_t)(fh * 64 + (l & 63)) * p.ldw;
+    if constexpr (kDual) wrow = ((l & 1) ? p.W2 : p.W1) + (int64_t)(fh * 64 + (l >> 1)) * p.ldw;   // interleaved lanes
     else wrow = p.W1 + (int64_t)(l < NOUT ? l : 0) * p.ldw;
     const bool zero_row = !kDual && l >= NOUT;
     const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
@@ -727,11 +726,9 @@ __global__ void __launch_bounds__(kV3Threads, 1) tf32x3_gemm_v3_kernel(const V2P
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     } else {
-      const int which = quad >> 1;
-      const int f = fh * 64 + (quad & 1) * 32 + lane;
-      const uint32_t my_x = sX + (uint32_t)warp * 4096u + (uint32_t)lane * 4u;
-      const uint32_t peer_x = sX + (uint32_t)(warp ^ 2) * 4096u + (uint32_t)lane * 4u;
-      const int bar_id = 1 + (quad & 1) * 2 + half;
+      // lane 2i: accumulator of W1 (a1) for feature f, lane 2i+1: accumulator of W2 (a2) for the same feature
+      const int kind = lane & 1;
+      const int f = fh * 64 + quad * 16 + (lane >> 1);
 #pragma unroll 1
       for (int64_t t = 0; t < my_tiles; ++t) {
         const int64_t rt = (tile0 + t * tstep) * kV3Rows + half * 64;     // first of this warp's 64 rows
@@ -739,8 +736,8 @@ __global__ void __launch_bounds__(kV3Threads, 1) tf32x3_gemm_v3_kernel(const V2P
         if constexpr (MODE == kV2DualSeparate) {
           mbar_wait(bar_acc_full + 8 * acc, acc_phase);
           tc_fence_after();
-          float* out = which ? p.D2 : p.D;
-          const int64_t ldo = which ? p.ldd2 : p.ldd;
+          float* out = kind ? p.D2 : p.D;
+          const int64_t ldo = kind ? p.ldd2 : p.ldd;
 #pragma unroll 1
           for (int c = 0; c < 2; ++c) {
             float v[32];
@@ -763,46 +760,48 @@ __global__ void __launch_bounds__(kV3Threads, 1) tf32x3_gemm_v3_kernel(const V2P
             }
           }
         } else {
-          // rows this warp finalises: 32 rows starting at r0 (acc1 warp: the first 32 of the pair's 64, acc2 warp: the rest)
-          const int64_t r0 = rt + which * 32;
-          const int nvalid = (int)((p.M - r0) < 32 ? (p.M - r0) : 32);     // warp-uniform, may be <= 0
-          float* dst = p.D + r0 * p.ldd + f;
+          // Of every 32-row chunk the even lane finalises rows 0..15 and the odd lane rows 16..31 of feature f: one
+          // shuffle per output swaps the half each lane does not finalise.  Same operations in the same order as the two
+          // launches this kernel replaces: (S + c*P) resp. ((old + a1) + c*a2).
+          const int64_t rmine = rt + kind * 16;                             // chunk c: rows rmine + 32 c + jj
+          float* dst = p.D + rmine * p.ldd + f;
           float old[32];
           if constexpr (MODE == kV2DualAccumulate) {
-            if (nvalid == 32) {
+            // requested before waiting for this tile's MMAs: the DRAM latency hides behind them
 #pragma unroll
-              for (int j = 0; j < 32; ++j) old[j] = dst[j * p.ldd];
-            } else {
+            for (int c = 0; c < 2; ++c)
 #pragma unroll
-              for (int j = 0; j < 32; ++j) old[j] = j < nvalid ? dst[j * p.ldd] : 0.0f;
-            }
+              for (int jj = 0; jj < 16; ++jj)
+                old[c * 16 + jj] = (rmine + c * 32 + jj < p.M) ? dst[(int64_t)(c * 32 + jj) * p.ldd] : 0.0f;
           }
-          float sc_l = 1.0f;
-          if (p.scale != nullptr && lane < nvalid) sc_l = __ldg(p.scale + r0 + lane);
+          float sc_l[2] = {1.0f, 1.0f};
+          if (p.scale != nullptr) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+              if (rt + c * 32 + lane < p.M) sc_l[c] = __ldg(p.scale + rt + c * 32 + lane);
+          }
           mbar_wait(bar_acc_full + 8 * acc, acc_phase);
           tc_fence_after();
           asm volatile("" : "+l"(dst));
-          // the partner has finished reading what I wrote for the previous tile
-          asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-          float v[32];
-          tmem_ld32(t_lane + (which ? 0 : 32), v);                  // the rows the partner finalises
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            asm volatile("st.shared.f32 [%0], %1;" ::"r"(my_x + j * 128), "f"(v[j]) : "memory");
-          tmem_ld32(t_lane + (which ? 32 : 0), v);                  // the rows this warp finalises
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_acc_empty + 8 * acc);
-          asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+          for (int c = 0; c < 2; ++c) {
+            float v[32];
+            tmem_ld32(t_lane + c * 32, v);
+            if (c == 1) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar_acc_empty + 8 * acc);
+            }
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float got = lds32(peer_x + j * 128);
-            const float a1 = which ? got : v[j];
-            const float a2 = which ? v[j] : got;
-            const float c = __shfl_sync(0xffffffffu, sc_l, j);
-            float r = (MODE == kV2DualAccumulate) ? __fadd_rn(old[j], a1) : a1;
-            r = __fadd_rn(r, __fmul_rn(c, a2));
-            if (j < nvalid) dst[j * p.ldd] = r;
+            for (int jj = 0; jj < 16; ++jj) {
+              const float got = __shfl_xor_sync(0xffffffffu, kind ? v[jj] : v[jj + 16], 1);
+              const float a1 = kind ? got : v[jj];
+              const float a2 = kind ? v[jj + 16] : got;
+              const float cs = __shfl_sync(0xffffffffu, sc_l[c], jj + kind * 16);
+              float r = (MODE == kV2DualAccumulate) ? __fadd_rn(old[c * 16 + jj], a1) : a1;
+              r = __fadd_rn(r, __fmul_rn(cs, a2));
+              if (rmine + c * 32 + jj < p.M) dst[(int64_t)(c * 32 + jj) * p.ldd] = r;
+            }
           }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }

@@ -3,10 +3,10 @@ usage: python scripts/ncu_roles.py <rep> <kernel regex> [launch index]"""
 import csv, io, subprocess, sys
 rep, rx = sys.argv[1], sys.argv[2]
 idx = int(sys.argv[3]) if len(sys.argv) > 3 else 0
-txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass", "-k", "regex:" + rx],
-                     capture_output=True, text=True).stdout
-blocks = txt.split('"Kernel Name"')[1:]
-rows = list(csv.reader(io.StringIO('"Kernel Name"' + blocks[idx])))
+txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass", "-k", "regex:" + rx,
+                      "--launch-skip", str(idx), "--launch-count", "1"], capture_output=True, text=True).stdout
+blocks = txt.split('"Kernel Name"')     # ncu prints every selected launch twice
+rows = list(csv.reader(io.StringIO('"Kernel Name"' + blocks[1])))
 hdr = rows[1]; ix = {h: i for i, h in enumerate(hdr)}
 data = [r for r in rows[2:] if len(r) == len(hdr)]
 S = lambda r: int(r[ix["# Samples"]] or 0)
