@@ -464,7 +464,10 @@ __global__ void __launch_bounds__(kV3Threads, 1) tf32x3_gemm_v3_kernel(const V2P
   // COMPILE-TIME on purpose: as launch parameters (swept in profiles/r2_gemm_sweep.txt: 1 lo slot -12 %, 3-4 no gain) the
   // run-time modulo in the single MMA-issuing thread cost 15-25 % of every projection
   constexpr int kV3LoSlots = 2;
-  constexpr int kV3HiSlots = kV3Slots - kV3LoSlots;
+  #ifndef DMP_V3_DUAL_SLOTS
+#define DMP_V3_DUAL_SLOTS kV3Slots
+#endif
+  constexpr int kV3HiSlots = (kDual ? DMP_V3_DUAL_SLOTS : kV3Slots) - kV3LoSlots;
   constexpr int kHalves = kDual ? NOUT / 64 : 1;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -764,21 +767,44 @@ __global__ void __launch_bounds__(kV3Threads, 1) tf32x3_gemm_v3_kernel(const V2P
           // shuffle per output swaps the half each lane does not finalise.  Same operations in the same order as the two
           // launches this kernel replaces: (S + c*P) resp. ((old + a1) + c*a2).
           const int64_t rmine = rt + kind * 16;                             // chunk c: rows rmine + 32 c + jj
+          const int nv = (int)((p.M - rmine) < 64 ? (p.M - rmine) : 64);    // rows c*32 + jj < nv exist (may be <= 0)
+          const bool full = rt + 64 <= p.M;                                 // warp-uniform fast path
           float* dst = p.D + rmine * p.ldd + f;
           float old[32];
           if constexpr (MODE == kV2DualAccumulate) {
             // requested before waiting for this tile's MMAs: the DRAM latency hides behind them
+            if (full) {
 #pragma unroll
-            for (int c = 0; c < 2; ++c)
+              for (int c = 0; c < 2; ++c)
 #pragma unroll
-              for (int jj = 0; jj < 16; ++jj)
-                old[c * 16 + jj] = (rmine + c * 32 + jj < p.M) ? dst[(int64_t)(c * 32 + jj) * p.ldd] : 0.0f;
+                for (int jj = 0; jj < 16; ++jj) old[c * 16 + jj] = dst[(int64_t)(c * 32 + jj) * p.ldd];
+            } else {
+#pragma unroll
+              for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int jj = 0; jj < 16; ++jj)
+                  old[c * 16 + jj] = (c * 32 + jj < nv) ? dst[(int64_t)(c * 32 + jj) * p.ldd] : 0.0f;
+            }
           }
           float sc_l[2] = {1.0f, 1.0f};
           if (p.scale != nullptr) {
 #pragma unroll
             for (int c = 0; c < 2; ++c)
               if (rt + c * 32 + lane < p.M) sc_l[c] = __ldg(p.scale + rt + c * 32 + lane);
+          }
+          if (t + 1 < my_tiles) {
+            // The epilogue is the critical path of the accumulate form and has no register room to hold the next tile's
+            // operands, so it asks L2 for them now (64-byte segment of rows lane, lane + 32; the row scales): the profile
+            // showed a fifth of the epilogue's time waiting for exactly these loads at DRAM latency.
+            const int64_t rn = rt + tstep * kV3Rows;
+            if constexpr (MODE == kV2DualAccumulate) {
+#pragma unroll
+              for (int c = 0; c < 2; ++c)
+                if (rn + c * 32 + lane < p.M)
+                  asm volatile("prefetch.global.L2 [%0];" ::"l"(p.D + (rn + c * 32 + lane) * p.ldd + fh * 64 + quad * 16));
+            }
+            if (p.scale != nullptr && lane < 2 && rn + lane * 32 < p.M)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.scale + rn + lane * 32));
           }
           mbar_wait(bar_acc_full + 8 * acc, acc_phase);
           tc_fence_after();
@@ -800,7 +826,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) tf32x3_gemm_v3_kernel(const V2P
               const float cs = __shfl_sync(0xffffffffu, sc_l[c], jj + kind * 16);
               float r = (MODE == kV2DualAccumulate) ? __fadd_rn(old[c * 16 + jj], a1) : a1;
               r = __fadd_rn(r, __fmul_rn(cs, a2));
-              if (rmine + c * 32 + jj < p.M) dst[(int64_t)(c * 32 + jj) * p.ldd] = r;
+              if (full || c * 32 + jj < nv) dst[(int64_t)(c * 32 + jj) * p.ldd] = r;
             }
           }
         }
