@@ -26,6 +26,8 @@
 // in quadrant q+2 -- different warps by the hardware's lane-quadrant rule -- so the two warps swap half of their rows
 // through shared memory (named barrier per pair) and each finalises 16 rows.  For N = 128 two CTAs (blockIdx parity =
 // feature half) walk the same tiles in the same order: the second read of a tile hits L2.
+#include <atomic>
+
 #include "tc_common.cuh"
 
 namespace dmp {
@@ -67,6 +69,7 @@ struct V2Params {
   int64_t M;
   int act; float slope;
   int use_tma;
+  unsigned int* tile_ctr;                          // v3: dynamic tile scheduler ([half 0, half 1, CTAs done]) or NULL = static
 };
 
 template <int MODE>
@@ -481,6 +484,13 @@ __global__ void __launch_bounds__(kV3Threads, 1) tf32x3_gemm_v3_kernel(const V2P
   const uint32_t bar_acc_full = sBar + 256;                   // 2
   const uint32_t bar_acc_empty = sBar + 272;                  // 2
   const uint32_t tmem_slot = sBar + 288;
+  // Tile queue: the TMA thread decides which tile comes next (statically strided, or from a global counter so that CTAs
+  // which start late -- an NCCL collective was holding their SM -- take only what is left) and publishes it here;
+  // every other role reads its tile ids from the queue.  Entry n is overwritten by entry n + kTileQ: by then the hi
+  // ring (<= 6 tiles) and the two accumulators guarantee that every role is past entry n + kTileQ - 8.
+  constexpr int kTileQ = 16;
+  const uint32_t bar_tile = sBar + 304;                       // 16: queue entry written
+  const uint32_t s_tile = sBar + 432;                         // 16 x int32: tile id, -1 = no more work
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5;
@@ -489,7 +499,6 @@ __global__ void __launch_bounds__(kV3Threads, 1) tf32x3_gemm_v3_kernel(const V2P
   const int64_t tile0 = (kHalves == 2) ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x;
   const int64_t tstep = (kHalves == 2) ? (int64_t)(gridDim.x >> 1) : (int64_t)gridDim.x;
   const int64_t num_tiles = (p.M + kV3Rows - 1) / kV3Rows;
-  const int64_t my_tiles = tile0 < num_tiles ? (num_tiles - tile0 + tstep - 1) / tstep : 0;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kV3HiSlots; ++s) {
@@ -504,6 +513,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) tf32x3_gemm_v3_kernel(const V2P
       mbar_init(bar_acc_full + 8 * a, 1);
       mbar_init(bar_acc_empty + 8 * a, kV2EpilogueWarps);
     }
+    for (int q = 0; q < kTileQ; ++q) mbar_init(bar_tile + 8 * q, 1);
     fence_barrier_init();
   }
   // TMEM map: [0,128) acc 0 | [128,256) acc 1 | [256,256+K) W hi | [256+K,256+2K) W lo
@@ -542,14 +552,31 @@ __global__ void __launch_bounds__(kV3Threads, 1) tf32x3_gemm_v3_kernel(const V2P
   __syncthreads();
   tc_fence_after();
 
+  // consumer side of the tile queue: n-th tile of this CTA, or -1
+  int tq = 0;
+  uint32_t tq_phase = 0;
+  auto next_tile = [&]() -> int64_t {
+    mbar_wait(bar_tile + 8 * tq, tq_phase);
+    const int32_t t = (int32_t)lds32u(s_tile + 4 * tq);
+    if (++tq == kTileQ) { tq = 0; tq_phase ^= 1; }
+    return (int64_t)t;
+  };
+
   if (warp == kV3TmaWarp) {
     // =========================== TMA ISSUER ===========================
     if (elect_one()) {   // (the warp arrives here converged)
-      int slot = 0;
+      int slot = 0, wq = 0;
       uint32_t sphase = 0;
+      int64_t tile = tile0;
 #pragma unroll 1
-      for (int64_t t = 0; t < my_tiles; ++t) {
-        const int r0 = (int)((tile0 + t * tstep) * kV3Rows);
+      for (;;) {
+        if (p.tile_ctr != nullptr) tile = (int64_t)atomicAdd(p.tile_ctr + fh, 1u);
+        const bool more = tile < num_tiles;
+        sts32u(s_tile + 4 * wq, more ? (uint32_t)tile : 0xffffffffu);
+        mbar_arrive(bar_tile + 8 * wq);                         // release: the entry is visible to whoever sees the phase
+        if (++wq == kTileQ) wq = 0;
+        if (!more) break;
+        const int r0 = (int)(tile * kV3Rows);
 #pragma unroll 1
         for (int kb = 0; kb < kKBlocks; ++kb) {
           mbar_wait(bar_empty_hi + 8 * slot, sphase ^ 1);       // the slot's previous tile has retired
@@ -557,6 +584,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) tf32x3_gemm_v3_kernel(const V2P
           tma_load_2d(sHi + slot * kV3SlotBytes, &tmap, kb * kKB, r0, bar_raw + 8 * slot);
           if (++slot == kV3HiSlots) { slot = 0; sphase ^= 1; }
         }
+        tile += tstep;
       }
     }
   } else if (warp > kV2MmaWarp) {
@@ -570,13 +598,17 @@ __global__ void __launch_bounds__(kV3Threads, 1) tf32x3_gemm_v3_kernel(const V2P
     int hs = 0, ls = 0;
     uint32_t hphase = 0, lphase = 0;
 #pragma unroll 1
-    for (int64_t g = 0; g < my_tiles * kKBlocks; ++g) {
+    for (;;) {
+     const int64_t tile = next_tile();
+     if (tile < 0) break;
+#pragma unroll 1
+     for (int kb = 0; kb < kKBlocks; ++kb) {
       mbar_wait(bar_raw + 8 * hs, hphase);                      // the raw k-block has landed
       mbar_wait(bar_empty_lo + 8 * ls, lphase ^ 1);             // the lo slot's previous user has retired
       const uint32_t hi = sHi + hs * kV3SlotBytes, lo = sLo + ls * kV3SlotBytes;
       float sc[4] = {1.0f, 1.0f, 1.0f, 1.0f};
       if (p.pre_scale != nullptr) {
-        const int64_t r0 = (tile0 + (g / kKBlocks) * tstep) * kV3Rows + row0;
+        const int64_t r0 = tile * kV3Rows + row0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) sc[i] = (r0 + 32 * i < p.M) ? __ldg(p.pre_scale + r0 + 32 * i) : 1.0f;
       }
@@ -602,6 +634,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) tf32x3_gemm_v3_kernel(const V2P
       if (lane == 0) mbar_arrive(bar_full_lo + 8 * ls);
       if (++hs == kV3HiSlots) { hs = 0; hphase ^= 1; }
       if (++ls == kV3LoSlots) { ls = 0; lphase ^= 1; }
+     }
     }
   } else if (warp == kV2MmaWarp) {
     // =========================== MMA ISSUER ===========================
@@ -609,7 +642,8 @@ __global__ void __launch_bounds__(kV3Threads, 1) tf32x3_gemm_v3_kernel(const V2P
     int acc = 0, ls = 0, hs0 = 0;                              // hs0: hi slot of the tile's first k-block
     uint32_t acc_phase = 0, lphase = 0;
 #pragma unroll 1
-    for (int64_t t = 0; t < my_tiles; ++t) {
+    for (;;) {
+      if (next_tile() < 0) break;
       mbar_wait(bar_acc_empty + 8 * acc, acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kV3Rows);
@@ -670,7 +704,9 @@ __global__ void __launch_bounds__(kV3Threads, 1) tf32x3_gemm_v3_kernel(const V2P
       const bool live = quad * 32 < NOUT;
       const float bias_f = (kNeedBias && live && p.bias != nullptr) ? __ldg(p.bias + f) : 0.0f;
 #pragma unroll 1
-      for (int64_t t = 0; t < my_tiles; ++t) {
+      for (;;) {
+        const int64_t tile = next_tile();
+        if (tile < 0) break;
         if (!live) {
           mbar_wait(bar_acc_full + 8 * acc, acc_phase);
           if (lane == 0) mbar_arrive(bar_acc_empty + 8 * acc);
@@ -680,7 +716,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) tf32x3_gemm_v3_kernel(const V2P
         const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kV3Rows + half * 64);
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
-          const int64_t r0 = (tile0 + t * tstep) * kV3Rows + half * 64 + c * 32;
+          const int64_t r0 = tile * kV3Rows + half * 64 + c * 32;
           const int nvalid = (int)((p.M - r0) < 32 ? (p.M - r0) : 32);     // warp-uniform, may be <= 0
           float* dst = p.D + r0 * p.ldd + f;
           float tt[32];
@@ -733,8 +769,10 @@ __global__ void __launch_bounds__(kV3Threads, 1) tf32x3_gemm_v3_kernel(const V2P
       const int kind = lane & 1;
       const int f = fh * 64 + quad * 16 + (lane >> 1);
 #pragma unroll 1
-      for (int64_t t = 0; t < my_tiles; ++t) {
-        const int64_t rt = (tile0 + t * tstep) * kV3Rows + half * 64;     // first of this warp's 64 rows
+      for (;;) {
+        const int64_t tile = next_tile();
+        if (tile < 0) break;
+        const int64_t rt = tile * kV3Rows + half * 64;                    // first of this warp's 64 rows
         const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kV3Rows + half * 64);
         if constexpr (MODE == kV2DualSeparate) {
           mbar_wait(bar_acc_full + 8 * acc, acc_phase);
@@ -792,19 +830,23 @@ __global__ void __launch_bounds__(kV3Threads, 1) tf32x3_gemm_v3_kernel(const V2P
             for (int c = 0; c < 2; ++c)
               if (rt + c * 32 + lane < p.M) sc_l[c] = __ldg(p.scale + rt + c * 32 + lane);
           }
-          if (t + 1 < my_tiles) {
-            // The epilogue is the critical path of the accumulate form and has no register room to hold the next tile's
-            // operands, so it asks L2 for them now (64-byte segment of rows lane, lane + 32; the row scales): the profile
-            // showed a fifth of the epilogue's time waiting for exactly these loads at DRAM latency.
-            const int64_t rn = rt + tstep * kV3Rows;
-            if constexpr (MODE == kV2DualAccumulate) {
+          // The epilogue is the critical path of the accumulate form and has no register room to hold the next tile's
+          // operands, so it asks L2 for them now (64-byte segment of rows lane, lane + 32; the row scales): the profile
+          // showed a fifth of the epilogue's time waiting for exactly these loads at DRAM latency.  The next tile id is
+          // taken from the queue only if the TMA thread has published it already (it runs 2-3 tiles ahead).
+          if (mbar_test(bar_tile + 8 * tq, tq_phase)) {
+            const int32_t tn = (int32_t)lds32u(s_tile + 4 * tq);
+            if (tn >= 0) {
+              const int64_t rn = (int64_t)tn * kV3Rows + half * 64;
+              if constexpr (MODE == kV2DualAccumulate) {
 #pragma unroll
-              for (int c = 0; c < 2; ++c)
-                if (rn + c * 32 + lane < p.M)
-                  asm volatile("prefetch.global.L2 [%0];" ::"l"(p.D + (rn + c * 32 + lane) * p.ldd + fh * 64 + quad * 16));
+                for (int c = 0; c < 2; ++c)
+                  if (rn + c * 32 + lane < p.M)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p.D + (rn + c * 32 + lane) * p.ldd + fh * 64 + quad * 16));
+              }
+              if (p.scale != nullptr && lane < 2 && rn + lane * 32 < p.M)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.scale + rn + lane * 32));
             }
-            if (p.scale != nullptr && lane < 2 && rn + lane * 32 < p.M)
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.scale + rn + lane * 32));
           }
           mbar_wait(bar_acc_full + 8 * acc, acc_phase);
           tc_fence_after();
@@ -838,6 +880,15 @@ __global__ void __launch_bounds__(kV3Threads, 1) tf32x3_gemm_v3_kernel(const V2P
   tc_fence_before();
   __syncthreads();
   if (warp == kV2MmaWarp) tmem_dealloc(tmem_base, kTmemCols);
+  if (p.tile_ctr != nullptr && threadIdx.x == 0) {
+    // every CTA has made its last fetch: the last one to get here leaves the counters zeroed for the next launch
+    __threadfence();
+    if (atomicAdd(p.tile_ctr + 2, 1u) == gridDim.x - 1) {
+      p.tile_ctr[0] = 0u; p.tile_ctr[1] = 0u;
+      __threadfence();
+      p.tile_ctr[2] = 0u;
+    }
+  }
 }
 
 // TMA descriptor of the streamed operand: fp32 [M rows x K], box = 64 rows x 32 floats, 128-byte swizzle
@@ -853,6 +904,38 @@ static bool make_tmap_rows64(CUtensorMap* tmap, const float* A, int64_t lda, int
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// Counters of the dynamic tile scheduler: [tiles handed out to feature half 0, half 1, CTAs finished, pad] per launch.
+// A launch leaves its triple zeroed (the last CTA resets it), so a slot can be reused by any later launch that cannot run
+// CONCURRENTLY with it: eager launches cycle through kCtrEager slots (1024 launches would have to be in flight for a
+// clash); launches recorded into a CUDA graph keep their slot for the life of the graph, so each gets one of its own
+// from a separate range and, when that range is used up, the launch falls back to the static schedule.
+constexpr int kCtrEager = 1024, kCtrPool = 4096;
+__device__ unsigned int g_tile_ctr[kCtrPool][4];
+
+static unsigned int* tile_counters(cudaStream_t stream) {
+  static const bool on = [] { const char* e = getenv("DMP_GEMM_DYNAMIC"); return e ? atoi(e) != 0 : true; }();
+  if (!on) return nullptr;
+  static unsigned int* base[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (base[dev] == nullptr) {
+    void* ptr = nullptr;
+    if (cudaGetSymbolAddress(&ptr, g_tile_ctr) != cudaSuccess) return nullptr;
+    base[dev] = static_cast<unsigned int*>(ptr);
+  }
+  static std::atomic<unsigned> next_eager{0}, next_captured{0};
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &st) != cudaSuccess) return nullptr;
+  unsigned slot;
+  if (st == cudaStreamCaptureStatusNone) {
+    slot = next_eager.fetch_add(1) % kCtrEager;
+  } else {
+    slot = kCtrEager + next_captured.fetch_add(1);
+    if (slot >= (unsigned)kCtrPool) return nullptr;
+  }
+  return base[dev] + 4 * slot;
+}
+
 static bool v3_enabled() {   // DMP_GEMM_V3=0: 64-row kernel everywhere (A/B runs)
   static const bool on = [] { const char* e = getenv("DMP_GEMM_V3"); return e ? atoi(e) != 0 : true; }();
   return on;
@@ -864,6 +947,7 @@ static int launch_v2_mode(const V2Params& p, cudaStream_t stream) {
   constexpr int kHalves = (MODE >= kV2DualStore) ? NOUT / 64 : 1;
   const int64_t streams = persistent_sms() / kHalves;
   V2Params q = p;
+  q.tile_ctr = nullptr;
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
   if (v3_enabled() && tma_enabled() && p.M >= kV3Rows && make_tmap_rows(&tmap, p.A, p.lda, p.M, K)) {
@@ -880,6 +964,7 @@ static int launch_v2_mode(const V2Params& p, cudaStream_t stream) {
     const int64_t tiles = (p.M + kV3Rows - 1) / kV3Rows;
     const unsigned grid = (unsigned)((tiles < streams ? tiles : streams) * kHalves);
     q.use_tma = 1;
+    q.tile_ctr = tile_counters(stream);
     tf32x3_gemm_v3_kernel<NOUT, K, MODE><<<grid, kV3Threads, kV3Smem, stream>>>(q, tmap);
     return launch_status("tf32x3_gemm_v3_kernel");
   }
