@@ -431,51 +431,45 @@ __global__ void __launch_bounds__(kTnThreads, 1) tf32x3_gemm_tn_kernel(const TnP
   if (warp == kTnMmaWarp) tmem_dealloc(tmem_base, kTnTmemCols);
 }
 
-// D[m, n] (+)= sum over CTAs (ascending) of partial[cta][n][m]
+// D[m, n] (+)= sum over CTAs of partial[cta][n][m]   (and the column sums), in a FIXED order: lane j of a group of four
+// adds the partials j, j+4, j+8, ... in ascending order, then (s0 + s1) + (s2 + s3).  The cost of this kernel is the
+// chain of dependent L2 round trips, not the adds (148 partials one after the other: 9.6 us; batches of 8: 7 us, a
+// tenth of a small-graph training step), so every output gets four lanes with 37 independent loads each.
+constexpr int kRedLanes = 4;
 __global__ void __launch_bounds__(256) tn_reduce_kernel(const float* __restrict__ partial, int parts, int M, int N,
                                                         float* __restrict__ D, int64_t ldd, int accumulate,
                                                         const float* __restrict__ part_sx, float* __restrict__ sum_x,
                                                         const float* __restrict__ part_sg, float* __restrict__ sum_g) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // over N*M, m fastest (coalesced partial reads)
-  if (idx >= M * N) {
-    const int j = idx - M * N;                               // tail threads: the column sums
-    const float* src = nullptr;
-    float* dst = nullptr;
-    int64_t step = 0;
-    if (j < M && sum_x != nullptr) { src = part_sx + j; dst = sum_x + j; step = M; }
-    else if (j >= M && j < M + N && sum_g != nullptr) { src = part_sg + (j - M); dst = sum_g + (j - M); step = N; }
-    if (src != nullptr) {
-      float s = 0.0f;
-      int c = 0;
-      for (; c + 8 <= parts; c += 8) {     // loads in batches of 8, adds in CTA order (see below)
-        float v[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = __ldcg(src + (int64_t)(c + u) * step);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) s = __fadd_rn(s, v[u]);
-      }
-      for (; c < parts; ++c) s = __fadd_rn(s, __ldcg(src + (int64_t)c * step));
-      *dst = s;
-    }
-    return;
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int idx = gid / kRedLanes, j = gid % kRedLanes;     // output (m fastest: neighbouring groups read one sector), lane
+  const float* src = nullptr;
+  float* dst = nullptr;
+  int64_t step = 0;
+  bool acc = false;
+  if (idx < M * N) {
+    src = partial + idx; step = (int64_t)M * N;
+    dst = D + (int64_t)(idx % M) * ldd + idx / M;
+    acc = accumulate != 0;
+  } else {
+    const int t = idx - M * N;                                // the column sums
+    if (t < M && sum_x != nullptr) { src = part_sx + t; dst = sum_x + t; step = M; }
+    else if (t >= M && t < M + N && sum_g != nullptr) { src = part_sg + (t - M); dst = sum_g + (t - M); step = N; }
   }
-  const int n = idx / M, m = idx % M;
-  // 148 partials added in CTA order; the loads of 8 partials are issued together (they are independent: the chain of
-  // dependent L2 round trips, not the adds, was the cost of this kernel: 9.6 us -> ~2 us), the adds stay sequential
   float s = 0.0f;
-  const float* src = partial + idx;
-  const int64_t step = (int64_t)M * N;
-  int c = 0;
-  for (; c + 8 <= parts; c += 8) {
-    float v[8];
+  if (src != nullptr) {
+    int c = j;
+    for (; c + 7 * kRedLanes < parts; c += 8 * kRedLanes) {
+      float v[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = __ldcg(src + (int64_t)(c + u) * step);
+      for (int u = 0; u < 8; ++u) v[u] = __ldcg(src + (int64_t)(c + u * kRedLanes) * step);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) s = __fadd_rn(s, v[u]);
+      for (int u = 0; u < 8; ++u) s = __fadd_rn(s, v[u]);
+    }
+    for (; c < parts; c += kRedLanes) s = __fadd_rn(s, __ldcg(src + (int64_t)c * step));
   }
-  for (; c < parts; ++c) s = __fadd_rn(s, __ldcg(src + (int64_t)c * step));
-  float* d = D + (int64_t)m * ldd + n;
-  *d = accumulate ? __fadd_rn(*d, s) : s;
+  s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, 1));
+  s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, 2));
+  if (src != nullptr && j == 0) *dst = acc ? __fadd_rn(*dst, s) : s;
 }
 
 template <int M, int N, bool SX, bool SG>
@@ -554,7 +548,7 @@ extern "C" int dmp_gemm_tn_tf32x3(const float* X, int64_t ldx, const float* row_
   else rc = launch_tn<64, 64>(p, (unsigned)grid, s);
   if (rc != DMP_OK) return rc;
   const int total = (int)(M * N + M + N);
-  tn_reduce_kernel<<<(total + 255) / 256, 256, 0, s>>>(p.partial, (int)grid, (int)M, (int)N, D, ldd, accumulate,
+  tn_reduce_kernel<<<(total * kRedLanes + 255) / 256, 256, 0, s>>>(p.partial, (int)grid, (int)M, (int)N, D, ldd, accumulate,
                                                       p.part_sx, colsum_x, p.part_sg, colsum_g);
   return launch_status("tn_reduce_kernel");
 }
