@@ -26,7 +26,8 @@
 // in quadrant q+2 -- different warps by the hardware's lane-quadrant rule -- so the two warps swap half of their rows
 // through shared memory (named barrier per pair) and each finalises 16 rows.  For N = 128 two CTAs (blockIdx parity =
 // feature half) walk the same tiles in the same order: the second read of a tile hits L2.
-#include <atomic>
+#include <mutex>
+#include <unordered_map>
 
 #include "tc_common.cuh"
 
@@ -904,34 +905,43 @@ static bool make_tmap_rows64(CUtensorMap* tmap, const float* A, int64_t lda, int
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// Counters of the dynamic tile scheduler: [tiles handed out to feature half 0, half 1, CTAs finished, pad] per launch.
-// A launch leaves its triple zeroed (the last CTA resets it), so a slot can be reused by any later launch that cannot run
-// CONCURRENTLY with it: eager launches cycle through kCtrEager slots (1024 launches would have to be in flight for a
-// clash); launches recorded into a CUDA graph keep their slot for the life of the graph, so each gets one of its own
-// from a separate range and, when that range is used up, the launch falls back to the static schedule.
+// Counters of the dynamic tile scheduler: [tiles handed out to feature half 0, half 1, CTAs finished, pad] per slot.
+// A launch leaves its slot zeroed (the last CTA resets it), so a slot may be shared by launches that can never run
+// CONCURRENTLY: eager launches get the slot of their STREAM (kernels of one stream are serialised); launches recorded
+// into a CUDA graph keep their slot for the life of the graph and may be replayed on any stream, so each gets one of
+// its own from a separate range.  When a range is used up the launch falls back to the static schedule.
 constexpr int kCtrEager = 1024, kCtrPool = 4096;
 __device__ unsigned int g_tile_ctr[kCtrPool][4];
 
 static unsigned int* tile_counters(cudaStream_t stream) {
   static const bool on = [] { const char* e = getenv("DMP_GEMM_DYNAMIC"); return e ? atoi(e) != 0 : true; }();
   if (!on) return nullptr;
+  static std::mutex mu;
   static unsigned int* base[64] = {};
+  static std::unordered_map<cudaStream_t, unsigned> slot_of_stream[64];
+  static unsigned next_captured = 0;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &st) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
   if (base[dev] == nullptr) {
     void* ptr = nullptr;
     if (cudaGetSymbolAddress(&ptr, g_tile_ctr) != cudaSuccess) return nullptr;
     base[dev] = static_cast<unsigned int*>(ptr);
   }
-  static std::atomic<unsigned> next_eager{0}, next_captured{0};
-  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
-  if (cudaStreamIsCapturing(stream, &st) != cudaSuccess) return nullptr;
   unsigned slot;
   if (st == cudaStreamCaptureStatusNone) {
-    slot = next_eager.fetch_add(1) % kCtrEager;
+    auto& map = slot_of_stream[dev];
+    auto it = map.find(stream);
+    if (it == map.end()) {
+      if (map.size() >= (size_t)kCtrEager) return nullptr;
+      it = map.emplace(stream, (unsigned)map.size()).first;
+    }
+    slot = it->second;
   } else {
-    slot = kCtrEager + next_captured.fetch_add(1);
-    if (slot >= (unsigned)kCtrPool) return nullptr;
+    if (next_captured >= (unsigned)(kCtrPool - kCtrEager)) return nullptr;
+    slot = kCtrEager + next_captured++;
   }
   return base[dev] + 4 * slot;
 }
