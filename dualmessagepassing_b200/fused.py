@@ -65,6 +65,9 @@ _ACT_NAME = {v: k for k, v in _ACT.items()}
 # below this many rows the persistent tcgen05 kernels' fixed cost (weight split per CTA, TMEM allocation, second
 # reduce launch) exceeds what cuBLAS sgemm needs for the whole product
 TC_MIN_ROWS = 16384
+# The K = rows reductions pay off much earlier: a 64 x 64 result over 2 771 rows takes cuBLAS sgemm 24 us (one CTA walks the
+# whole K), 82 us over 20 516 rows; the reduction kernel spreads K over the SMs (5-7 us + a 4 us fixed-order second pass).
+TN_MIN_ROWS = 2048
 # same-operand projection pairs in ONE launch (dmp_gemm_tf32x3_dual); False = two dmp_gemm_tf32x3 launches (A/B runs)
 DUAL_GEMM = __import__("os").environ.get("DMP_DUAL_GEMM", "1") != "0"
 
@@ -106,7 +109,7 @@ def _tnmm(X, G, *, row_scale=None, colsum_x=False, colsum_g=False):
     """(row_scale ⊙ X).T @ G -- the K = rows long weight-gradient reduction; tensor cores when both widths allow.
     colsum_x / colsum_g: also return X.sum(0) / G.sum(0) (bias gradients) -> (D, sum_x, sum_g)."""
     want_sums = colsum_x or colsum_g
-    if (DENSE_BACKEND == "auto" and X.shape[0] >= TC_MIN_ROWS and X.shape[1] in (64, 128) and G.shape[1] in (64, 128)
+    if (DENSE_BACKEND == "auto" and X.shape[0] >= min(TN_MIN_ROWS, TC_MIN_ROWS) and X.shape[1] in (64, 128) and G.shape[1] in (64, 128)
             and _dense_ok(X) and _dense_ok(G)):
         return gemm_tn_tf32x3(X, G, row_scale=row_scale, colsum_x=colsum_x, colsum_g=colsum_g)
     Xs = X * row_scale.reshape(-1, 1) if row_scale is not None else X

@@ -195,9 +195,12 @@ class SubgraphCountingModel(nn.Module):
         self.pred_fc2 = nn.Linear(hidden + 4, 1)
         self.act = nn.LeakyReLU(1 / 5.5)
 
+    def _labels(self, g):
+        return g.ndata[NODELABEL], g.edata[EDGELABEL] + g.edata[REVFLAG].long() * self.num_elabels
+
     def _embed(self, g):
-        el = g.edata[EDGELABEL] + g.edata[REVFLAG].long() * self.num_elabels
-        return self.vl_emb(g.ndata[NODELABEL]), self.el_emb(el)
+        vl, el = self._labels(g)
+        return label_embedding(self.vl_emb.weight, vl), label_embedding(self.el_emb.weight, el)
 
     def _pool(self, x, g):
         """Per-graph sum of node rows: nodes of a graph are contiguous -> sorted segments, no atomics."""
@@ -218,23 +221,82 @@ class SubgraphCountingModel(nn.Module):
         pres_v.index_put_((pattern.ndata["graph_id"], pattern.ndata[NODELABEL]),
                           torch.ones((), device=graph.device))     # (a device scalar: capturable in a CUDA graph)
         v_gate = pres_v[graph.ndata["graph_id"], graph.ndata[NODELABEL]]
-        p_v, p_e = self._embed(pattern)
-        g_v, g_e = self._embed(graph)
         if union is None:
+            p_v, p_e = self._embed(pattern)
+            g_v, g_e = self._embed(graph)
             p_v, p_e = self.rep.get_pattern_rep(pattern, p_v, p_e)
             g_v, g_e = self.rep.get_graph_rep(graph, g_v, g_e, v_gate=v_gate)
         else:
-            np_, ne_ = p_v.shape[0], p_e.shape[0]
+            # one lookup per table over the concatenated labels: the union's feature rows come out in place
+            (p_vl, p_el), (g_vl, g_el) = self._labels(pattern), self._labels(graph)
+            np_ = p_vl.shape[0]
             gate = torch.cat([torch.ones(np_, device=v_gate.device), v_gate])
-            u_v, u_e = self.rep.get_graph_rep(union, torch.cat([p_v, g_v]), torch.cat([p_e, g_e]), v_gate=gate)
+            u_v, u_e = self.rep.get_graph_rep(union, label_embedding(self.vl_emb.weight, torch.cat([p_vl, g_vl])),
+                                              label_embedding(self.el_emb.weight, torch.cat([p_el, g_el])), v_gate=gate)
             p_v, g_v = u_v[:np_], u_v[np_:]
-        p = self._pool(self.p_fc(p_v), pattern)
-        g = self._pool(self.g_fc(g_v), graph)
+        p = self._pool(row_linear(p_v, self.p_fc), pattern)
+        g = self._pool(row_linear(g_v, self.g_fc), graph)
         pl = pattern.batch_num_nodes().float().view(-1, 1)
         gl = graph.batch_num_nodes().float().view(-1, 1)
         extra = [pl, gl, 1.0 / pl, 1.0 / gl]
         y = self.act(self.pred_fc1(torch.cat([p, g, g - p, g * p] + extra, dim=1)))
         return self.pred_fc2(torch.cat([y] + extra, dim=1)).view(-1)
+
+
+class _LabelEmbedding(torch.autograd.Function):
+    """`weight[labels]` (nn.Embedding of node / edge labels, train.py:299-350) with a backward that suits a vocabulary of
+    a few dozen labels and 10^5 rows: dW = onehot(labels)^T @ g as ONE K = rows reduction on the tensor cores
+    (exact products with 0/1, deterministic) instead of torch's sort + unique-by-key + segment kernels (8 radix passes per
+    lookup: 13 % of the small-graph training step)."""
+
+    @staticmethod
+    def forward(ctx, weight, labels):
+        ctx.save_for_backward(labels)
+        ctx.vocab = weight.shape[0]
+        return weight.index_select(0, labels)
+
+    @staticmethod
+    def backward(ctx, g):
+        from .fused import _tnmm
+        (labels,) = ctx.saved_tensors
+        L = ctx.vocab
+        width = 64 if L <= 64 else 128 if L <= 128 else L      # the reduction kernel takes 64 / 128 columns
+        onehot = torch.zeros((labels.numel(), width), dtype=g.dtype, device=g.device)
+        onehot.scatter_(1, labels.view(-1, 1), 1.0)
+        dW = _tnmm(onehot, g.contiguous()) if g.is_cuda else onehot.t() @ g
+        return dW[:L], None
+
+
+class _RowLinear(torch.autograd.Function):
+    """nn.Linear over node rows (the predict net's p_layer / g_layer, pred.py:95-112) on the layer's own projection
+    kernels: bias in the GEMM epilogue, dW and db from ONE K = rows reduction (torch: addmm + mm + a 64 x 64 sgemm whose
+    single CTA walks all 20 k rows -- 82 us -- + a column sum)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        from .fused import _rowmm
+        x = x.contiguous()
+        ctx.save_for_backward(x, weight)
+        return _rowmm(x, weight, bias=bias)
+
+    @staticmethod
+    def backward(ctx, g):
+        from .fused import _rowmm, _tnmm
+        x, weight = ctx.saved_tensors
+        g = g.contiguous()
+        dx = _rowmm(g, weight.t().contiguous()) if ctx.needs_input_grad[0] else None
+        dw, db, _ = _tnmm(g, x, colsum_x=True)
+        return dx, dw, db
+
+
+def row_linear(x, linear):
+    if not x.is_cuda:
+        return linear(x)
+    return _RowLinear.apply(x, linear.weight, linear.bias)
+
+
+def label_embedding(weight, labels):
+    return _LabelEmbedding.apply(weight, labels)
 
 
 def union_graph(pattern, graph):

@@ -161,3 +161,28 @@ def test_len_to_mask_and_deferred_scalars_cpu():
         d.add(loss=torch.tensor(float(i)), reg=torch.tensor(2.0 * i))
     out = d.fetch()
     assert out == {"loss": [0.0, 1.0, 2.0], "reg": [0.0, 2.0, 4.0]} and d.fetch() == {}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows,vocab,width", [(50_000, 32, 64), (3_000, 7, 128), (20_000, 100, 64)])
+def test_label_embedding_matches_nn_embedding(rows, vocab, width):
+    """train_step.label_embedding: same rows forward, dW = onehot^T g (tensor-core reduction for >= 16384 rows) backward."""
+    from dualmessagepassing_b200 import _lib
+    from dualmessagepassing_b200.train_step import label_embedding
+    g = torch.Generator(device="cuda").manual_seed(rows + vocab)
+    labels = torch.randint(0, vocab, (rows,), device="cuda", generator=g)
+    w = torch.randn(vocab, width, device="cuda", generator=g)
+    up = torch.randn(rows, width, device="cuda", generator=g)
+    w1, w2 = w.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    _lib.PROFILE = []
+    out = label_embedding(w1, labels)
+    out.backward(up)
+    tags, _lib.PROFILE = {t[0] for t in _lib.PROFILE}, None
+    ref = torch.nn.functional.embedding(labels, w2)
+    ref.backward(up)
+    assert torch.equal(out, ref)
+    want = torch.zeros(vocab, width, dtype=torch.float64, device="cuda").index_add_(0, labels, up.double())
+    scale = float(want.abs().max())
+    assert float((w1.grad.double() - want).abs().max()) <= 1e-5 * scale
+    assert float((w1.grad.double() - want).abs().max()) <= 4 * float((w2.grad.double() - want).abs().max()) + 2e-6 * scale
+    assert ("gemm_tn_tf32x3" in tags) == (rows >= 2048)
