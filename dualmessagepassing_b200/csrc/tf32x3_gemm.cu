@@ -450,13 +450,12 @@ __global__ void __launch_bounds__(kV2Threads, 1) tf32x3_gemm_v2_kernel(const V2P
 constexpr int kV3Rows = 128;
 constexpr int kV3Threads = 18 * 32;
 constexpr int kV3TmaWarp = 17;
-constexpr int kV3MaxLoSlots = 4;
 constexpr int kV3SlotBytes = kV3Rows * 128;         // 16 KB: 128 rows x 32 floats
 // 224 KB of k-block slots (14) for every form.  The dual forms interleave the two weight matrices lane by lane
 // (TMEM lane 2i = row f0+i of W1, lane 2i+1 = the same row of W2), so the two accumulators of a feature sit in
 // NEIGHBOURING LANES OF ONE WARP and the epilogue combines them with shuffles -- the earlier layout (lanes 0..63 / 64..127)
 // put them in different warps and cost a 32 KB exchange buffer, two named barriers and 64 KB of shared-memory traffic per tile.
-constexpr int kV3Slots = 14, kV3MaxHiSlots = 12;
+constexpr int kV3Slots = 14;
 constexpr int kV3Smem = kV3Slots * kV3SlotBytes + 512 + 1024;
 
 template <int NOUT, int K, int MODE>
@@ -468,10 +467,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) tf32x3_gemm_v3_kernel(const V2P
   // COMPILE-TIME on purpose: as launch parameters (swept in profiles/r2_gemm_sweep.txt: 1 lo slot -12 %, 3-4 no gain) the
   // run-time modulo in the single MMA-issuing thread cost 15-25 % of every projection
   constexpr int kV3LoSlots = 2;
-  #ifndef DMP_V3_DUAL_SLOTS
-#define DMP_V3_DUAL_SLOTS kV3Slots
-#endif
-  constexpr int kV3HiSlots = (kDual ? DMP_V3_DUAL_SLOTS : kV3Slots) - kV3LoSlots;
+  constexpr int kV3HiSlots = kV3Slots - kV3LoSlots;          // 12: the barrier block below holds exactly that many
   constexpr int kHalves = kDual ? NOUT / 64 : 1;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
