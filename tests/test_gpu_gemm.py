@@ -140,3 +140,62 @@ def test_gemm_tn_column_sums(M, N):
     torch.testing.assert_close(sg.double(), G.double().sum(0), rtol=1e-6, atol=1e-6 * float(G.double().sum(0).abs().max()))
     ref = (c.double().unsqueeze(1) * X.double()).t() @ G.double()
     assert float((D.double() - ref).abs().max() / ref.abs().max()) <= 1e-5
+
+
+def test_tile_scheduler_static_and_dynamic_agree_bitwise():
+    """The projection kernels draw their tiles from a global counter (DMP_GEMM_DYNAMIC, default on); which CTA computes
+    which tile must not change a single bit.  The switch is read once per process, hence the subprocess."""
+    import os, subprocess, sys
+    code = (
+        "import torch, sys; sys.path.insert(0, '.');"
+        "from dualmessagepassing_b200 import functional as F;"
+        "g = torch.Generator(device='cuda').manual_seed(7);"
+        "A = torch.randn(200_003, 128, device='cuda', generator=g); W = torch.randn(128, 128, device='cuda', generator=g);"
+        "W2 = torch.randn(128, 128, device='cuda', generator=g); c = torch.rand(200_003, device='cuda', generator=g);"
+        "a = F.gemm_tf32x3(A, W, bias=W[0].contiguous(), act='leaky_relu', slope=0.2);"
+        "b = F.gemm_tf32x3_dual(A, W, W2, row_scale=c, mode='store');"
+        "print(float(a.double().sum()), float(a.double().abs().sum()), float(b.double().sum()), float(b.double().abs().sum()))")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for dyn in ("0", "1"):
+        env = dict(os.environ, DMP_GEMM_DYNAMIC=dyn)
+        outs.append(subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True,
+                                   timeout=300).stdout.strip())
+    assert outs[0] and outs[0] == outs[1], outs
+
+
+def test_tile_counters_reset_across_graph_replays_and_eager_launches():
+    """A launch leaves its tile counters zeroed: the same captured launches replayed many times, interleaved with eager
+    launches on the same and on another stream, keep giving the eager result."""
+    from dualmessagepassing_b200 import functional as F
+    g = torch.Generator(device="cuda").manual_seed(11)
+    A = torch.randn(70_001, 64, device="cuda", generator=g)
+    W1 = torch.randn(64, 64, device="cuda", generator=g)
+    W2 = torch.randn(64, 64, device="cuda", generator=g)
+    c = torch.rand(70_001, device="cuda", generator=g)
+    want1, want2 = F.gemm_tf32x3(A, W1), F.gemm_tf32x3_dual(A, W1, W2, row_scale=c, mode="store")
+    out1, out2 = torch.empty_like(want1), torch.empty_like(want2)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):      # warm-up outside capture (lazy module state)
+            F.gemm_tf32x3(A, W1, out=out1)
+            F.gemm_tf32x3_dual(A, W1, W2, row_scale=c, mode="store", out=out2)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        F.gemm_tf32x3(A, W1, out=out1)
+        F.gemm_tf32x3_dual(A, W1, W2, row_scale=c, mode="store", out=out2)
+        F.gemm_tf32x3(A, W1, out=out1)
+    for i in range(6):
+        out1.zero_(); out2.zero_()
+        graph.replay()
+        if i % 2:
+            with torch.cuda.stream(side):
+                other = F.gemm_tf32x3(A, W2)
+            eager = F.gemm_tf32x3(A, W1)
+            assert torch.equal(eager, want1)
+        torch.cuda.synchronize()
+        assert torch.equal(out1, want1) and torch.equal(out2, want2), i
+        if i % 2:
+            assert torch.equal(other, F.gemm_tf32x3(A, W2))
