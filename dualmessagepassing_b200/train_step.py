@@ -286,7 +286,7 @@ class _RowLinear(torch.autograd.Function):
         g = g.contiguous()
         dx = _rowmm(g, weight.t().contiguous()) if ctx.needs_input_grad[0] else None
         dw, db, _ = _tnmm(g, x, colsum_x=True)
-        return dx, dw, db
+        return dx, dw, (db if ctx.needs_input_grad[2] else None)
 
 
 def row_linear(x, linear):
