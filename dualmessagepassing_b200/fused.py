@@ -65,9 +65,10 @@ _ACT_NAME = {v: k for k, v in _ACT.items()}
 # below this many rows the persistent tcgen05 kernels' fixed cost (weight split per CTA, TMEM allocation, second
 # reduce launch) exceeds what cuBLAS sgemm needs for the whole product
 TC_MIN_ROWS = 16384
-# The K = rows reductions pay off much earlier: a 64 x 64 result over 2 771 rows takes cuBLAS sgemm 24 us (one CTA walks the
-# whole K), 82 us over 20 516 rows; the reduction kernel spreads K over the SMs (5-7 us + a 4 us fixed-order second pass).
-TN_MIN_ROWS = 2048
+# The K = rows reductions pay off much earlier: a 64 x 64 result over 1 856 rows takes cuBLAS sgemm 15 us (one CTA walks the
+# whole K), 24 us over 2 771 rows, 82 us over 20 516, and the bias gradients need a 13 us column-sum kernel on top; the
+# reduction kernel spreads K over the SMs (3-7 us + a 4 us fixed-order second pass) and returns the column sums for free.
+TN_MIN_ROWS = 512
 # same-operand projection pairs in ONE launch (dmp_gemm_tf32x3_dual); False = two dmp_gemm_tf32x3 launches (A/B runs)
 DUAL_GEMM = __import__("os").environ.get("DMP_DUAL_GEMM", "1") != "0"
 

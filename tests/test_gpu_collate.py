@@ -185,4 +185,4 @@ def test_label_embedding_matches_nn_embedding(rows, vocab, width):
     scale = float(want.abs().max())
     assert float((w1.grad.double() - want).abs().max()) <= 1e-5 * scale
     assert float((w1.grad.double() - want).abs().max()) <= 4 * float((w2.grad.double() - want).abs().max()) + 2e-6 * scale
-    assert ("gemm_tn_tf32x3" in tags) == (rows >= 2048)
+    assert ("gemm_tn_tf32x3" in tags) == (rows >= 512)
