@@ -539,7 +539,7 @@ def run_train(args, dev, world, rank, config, hbm_peak):
     return {"metric": "train graphs/sec (pattern/graph pairs)", "value": cfg["pairs"] * world / sec, "unit": "pairs/s",
             "ms_per_step": sec * 1e3, "steps": args.train_steps, "pairs_per_gpu": cfg["pairs"], "n_gpus": world,
             "scaling": "weak", "config": "BASELINE configs[%d] (%s): 3 shared DMP layers, hidden %d, sum-pool head, "
-            "MSE, AdamW(amsgrad)" % ({"cfg1": 0, "cfg2": 1, "cfg3": 2}[config], config, cfg["hidden"]),
+            "MSE, AdamW(amsgrad, fused kernel)" % ({"cfg1": 0, "cfg2": 1, "cfg3": 2}[config], config, cfg["hidden"]),
             "h2d_bytes_per_step": int(h2d), "dmp_launches_per_step": (_lib.LAUNCHES - l0) / args.train_steps,
             "cuda_graph": None if graphed is None else {
                 "replays_per_step": 1, "dmp_kernels_in_graph": graphed.dmp_kernels_in_graph,
